@@ -1,0 +1,169 @@
+/*
+ * tina_b200.h -- C ABI of the B200-native triangle-raster hot path.
+ *
+ * The reference (taichi-dev/taichi_three, "Tina") has NO FFI boundary: its
+ * rasteriser is a set of Taichi-JIT'd Python classes.  This header is the
+ * boundary a maintainer would bind (ctypes / pybind / cgo) to replace
+ *
+ *     tina/core/engine.py:5-76      Engine          (depth, W2V/V2W, bias)
+ *     tina/core/triangle.py:4-153   TriangleRaster  (set_object / render_occup / render_color)
+ *     tina/core/shader.py:112-148   Shader / ShaderGroup
+ *     tina/core/lighting.py:25-98   Lighting
+ *     tina/matr/material.py         Lambert / Phong / CookTorrance / Mix / Scale / Add / Emission
+ *     tina/postp/tonemap.py:9-12    ToneMapping.apply
+ *
+ * Conventions
+ *   - extern "C", no exceptions; every call returns 0 on success, <0 on error,
+ *     tina_last_error() gives a thread-local message.
+ *   - All pointers are DEVICE pointers unless the name ends in `_host`.
+ *   - Every launch takes a cudaStream_t (as void*) and is asynchronous.
+ *   - Image-like buffers are x-major like the reference's fields
+ *     (`ti.field(int, (W, H))`, triangle.py:16): element (x, y) lives at x*H + y.
+ *   - Handles are not thread-safe; distinct handles are independent.
+ *
+ * Visibility key (replaces Engine.depth + TriangleRaster.occup, engine.py:11,
+ * triangle.py:16): one signed 64-bit word per pixel,
+ *     key = ((int64)depth << 32) | (uint32)(face_base + f + 1)
+ * merged with a signed atomicMin.  Smaller depth wins; at equal depth the lower
+ * global face id wins, which is exactly the serial outcome of triangle.py:123-125
+ * (strict `>`), including "a later object only wins with strictly smaller depth".
+ * Low word 0 = "no face".  face_base is the number of faces rasterised since the
+ * last tina_clear_depth, so no per-object reset pass is needed.
+ */
+#ifndef TINA_B200_H
+#define TINA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct TinaEngine TinaEngine;
+typedef struct TinaRaster TinaRaster;
+
+/* raster option bits: TriangleRaster.__init__ kwargs (triangle.py:6-7) */
+#define TINA_SMOOTHING 1u
+#define TINA_TEXTURING 2u
+#define TINA_CULLING   4u
+#define TINA_CLIPPING  8u
+
+/* tina_render_color flags */
+#define TINA_COLOR_TONEMAP 1u /* fuse aces_tonemap (advans.py:32-35) into the store            */
+#define TINA_COLOR_FILL_BG 2u /* also write `bg` to pixels this object does not own (raster.py:176) */
+
+/* rasteriser strategy knobs (tina_raster_set_tuning): all settings give identical bits */
+#define TINA_TUNE_DEFAULT (-1)
+
+#define TINA_MAX_LIGHTS 16 /* lighting.py:26 */
+#define TINA_MAX_INSTR 96
+#define TINA_MAX_TEX 4
+
+/* Lighting (lighting.py:25-98).  dirs[i] = (x,y,z,w): w=0 directional (already
+ * normalised by the host, lighting.py:60-62), w=1 point light. */
+typedef struct {
+    float dirs[TINA_MAX_LIGHTS][4];
+    float colors[TINA_MAX_LIGHTS][4];
+    float ambient[4];
+    int32_t nlights;
+    int32_t pad[3];
+} TinaLighting;
+
+/* Material program: the reference's compile-time node graph (matr/nodes.py,
+ * matr/material.py) flattened by the host into postfix code over a vec3 stack.
+ * Scalars are broadcast to vec3 (identical arithmetic per component). */
+enum {
+    TINA_OP_CONST = 0,   /* push c                                                     nodes.py:42-49  */
+    TINA_OP_INPUT = 1,   /* push input[arg]: 0 pos, 1 color, 2 normal, 3 texcoord      nodes.py:79-96  */
+    TINA_OP_TEXTURE = 2, /* pop uv; push bilerp(tex[arg], uv*(shape-1))                nodes.py:99-111 */
+    TINA_OP_FRESNEL = 3, /* pop specular, albedo, metallic; push f0                    material.py:69-83 */
+    TINA_OP_LAMBERT = 4, /* push 1/pi                                                  material.py:392 */
+    TINA_OP_PHONG = 5,   /* pop shineness; push VoR**m*(m+2)/2                         material.py:450-454 */
+    TINA_OP_COOK = 6,    /* pop fresnel, roughness; push F*G*D                         material.py:323-362 */
+    TINA_OP_MIX = 7,     /* pop b, a, fac; push (1-fac)*a + fac*b                      material.py:96-118 */
+    TINA_OP_MUL = 8,     /* pop wei, fac; push fac*wei                                 material.py:157-176 */
+    TINA_OP_ADD = 9,     /* pop b, a; push a+b                                         material.py:204-220 */
+};
+
+typedef struct {
+    int32_t op;
+    int32_t arg;
+    float c[3];
+} TinaInstr;
+
+typedef struct {
+    /* three programs laid out back to back in `code`:
+     * [0, n_brdf) brdf(n, l, v); then n_ambient of ambient(); then n_emission of emission() */
+    int32_t n_brdf, n_ambient, n_emission, ntex;
+    const float *tex[TINA_MAX_TEX]; /* device, [w][h][c] f32, x-major (advans.py:8-28) */
+    int32_t tex_w[TINA_MAX_TEX], tex_h[TINA_MAX_TEX], tex_c[TINA_MAX_TEX];
+    TinaInstr code[TINA_MAX_INSTR];
+} TinaMaterial;
+
+const char *tina_last_error(void);
+int tina_version(void);
+
+/* ---- Engine (core/engine.py) ------------------------------------------------ */
+/* engine.py:6-28: owns the per-pixel key buffer (depth + winner), W2V/V2W (init
+ * diag(1,1,-1,1)), bias (.5,.5). */
+int tina_engine_create(TinaEngine **out, int device, int W, int H);
+int tina_engine_destroy(TinaEngine *e);
+/* engine.py:72-76 (host already did proj@view and inv in f64, cast to f32, row-major) */
+int tina_engine_set_camera(TinaEngine *e, const float *W2V_host, const float *V2W_host);
+/* engine.py:31-39 */
+int tina_engine_set_bias(TinaEngine *e, float bx, float by);
+/* engine.py:68-70: depth := 2**30, winner := none, face_base := 0 */
+int tina_engine_clear_depth(TinaEngine *e, void *stream);
+/* int64 keys[W*H]; the high words are Engine.depth viewed with stride 2 */
+int tina_engine_keys(TinaEngine *e, int64_t **keys);
+/* materialise Engine.depth as a dense int32[W*H] */
+int tina_engine_depth(TinaEngine *e, int32_t *depth, void *stream);
+/* sort-last support: every later face id is offset by `base` (global ids across ranks) */
+int tina_engine_set_face_base(TinaEngine *e, uint32_t base);
+int tina_engine_get_face_base(TinaEngine *e, uint32_t *base_host);
+
+/* ---- TriangleRaster (core/triangle.py) --------------------------------------- */
+int tina_raster_create(TinaRaster **out, TinaEngine *e, int64_t maxfaces, uint32_t flags);
+int tina_raster_destroy(TinaRaster *r);
+/* set_object for SimpleMesh-like sources (triangle.py:72-86, mesh/simple.py:33-47):
+ * verts [N,3,3], norms [N,3,3] (iff SMOOTHING), coors [N,3,2] (iff TEXTURING).
+ * borrow=1 aliases the caller's buffers (zero-copy) until the next set_faces*. */
+int tina_raster_set_faces(TinaRaster *r, const float *verts, const float *norms, const float *coors,
+                          int64_t nfaces, int borrow, void *stream);
+/* set_object for MeshModel (+MeshTransform, +MeshNoCulling/FlipCulling/FlipNormal):
+ * mesh/model.py:56-73, mesh/trans.py:28-40, mesh/cull.py:6-57.
+ * faces [N,3,3] int32 = [corner][v, vt, vn].  trans_host / trans_normal_host may be NULL.
+ * mode bits: 1 = double sided (MeshNoCulling), 2 = flip winding (MeshFlipCulling),
+ *            4 = negate normals (MeshFlipNormal). */
+int tina_raster_set_faces_indexed(TinaRaster *r, const float *v, const float *vt, const float *vn,
+                                  const int32_t *faces, int64_t nfaces, const float *trans_host,
+                                  const float *trans_normal_host, uint32_t mode, void *stream);
+/* set_object for MeshGrid (mesh/grid.py:26-58): pos [nx,ny,3]; recomputes the
+ * per-vertex normals like MeshGrid.pre_compute, texcoords (i/(nx-1), j/(ny-1)). */
+int tina_raster_set_faces_grid(TinaRaster *r, const float *pos, int nx, int ny, const float *trans_host,
+                               const float *trans_normal_host, uint32_t mode, void *stream);
+/* triangle.py:89-131 */
+int tina_raster_render_occup(TinaRaster *r, void *stream);
+/* triangle.py:134-153 + shader.py:119-131 + lighting.py:84-98; image [W,H,3] f32 */
+int tina_raster_render_color(TinaRaster *r, const TinaMaterial *mat_host, const TinaLighting *light_host,
+                             float *image, uint32_t flags, const float *bg_host, void *stream);
+/* materialise TriangleRaster.occup as int32[W*H] (-1 = none) for the last render_occup */
+int tina_raster_occup(TinaRaster *r, int32_t *occup, void *stream);
+/* device views of the current object's attribute buffers (may be NULL) */
+int tina_raster_buffers(TinaRaster *r, const float **verts, const float **norms, const float **coors,
+                        int64_t *nfaces);
+/* strategy knobs; which: 0 = max bbox area rasterised per thread, 1 = max bbox area
+ * rasterised per warp, 2 = force every face through the binned tile path */
+int tina_raster_set_tuning(TinaRaster *r, int which, int value);
+/* counters of the last render_occup (synchronises): faces culled, clipped, per-thread,
+ * per-warp, queued for the tile path, tile-list entries */
+int tina_raster_stats(TinaRaster *r, int64_t *out6_host);
+
+/* ---- frame glue (scene/raster.py:176,202-203) -------------------------------- */
+int tina_image_fill(float *image, int64_t npixels, const float *rgb_host, void *stream);
+int tina_image_tonemap(float *image, int64_t nfloats, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,194 @@
+"""ctypes wrapper of the CPU oracle (oracle/tina_oracle.c) -- TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+may import this module; the product package taichi_three_b200 never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libtina_oracle.so')
+
+SMOOTHING, TEXTURING, CULLING, CLIPPING = 1, 2, 4, 8
+
+_lib = None
+
+
+def build(force=False):
+    src = os.path.join(_HERE, 'tina_oracle.c')
+    if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < os.path.getmtime(src):
+        subprocess.run(['make', '-C', _HERE, 'libtina_oracle.so'], check=True, capture_output=True)
+    return LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(LIB_PATH)
+        _lib.orc_num_threads.restype = C.c_int
+    return _lib
+
+
+def _f(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def num_threads():
+    return lib().orc_num_threads()
+
+
+def clear_depth(W, H):
+    return np.full((W, H), 2**30, dtype=np.int32)
+
+
+def render_occup(verts, W2V, W, H, flags=CULLING | CLIPPING, bias=(0.5, 0.5), depth=None, parallel=False):
+    """-> (occup[W,H] i32, depth[W,H] i32 (updated copy), tie[W,H] u8, stats dict).  Serial = deterministic."""
+    verts = _f(verts).reshape(-1, 9)
+    W2V, bias = _f(W2V).reshape(16), _f(bias)
+    depth = clear_depth(W, H) if depth is None else np.ascontiguousarray(depth, dtype=np.int32).copy()
+    occup = np.empty((W, H), dtype=np.int32)
+    if parallel:
+        lib().orc_render_occup_parallel(_p(verts), C.c_int64(len(verts)), _p(W2V), _p(bias), W, H, C.c_uint32(flags),
+                                        _p(depth), _p(occup))
+        return occup, depth, None, {}
+    tie = np.zeros((W, H), dtype=np.uint8)
+    stats = np.zeros(5, dtype=np.int64)
+    lib().orc_render_occup(_p(verts), C.c_int64(len(verts)), _p(W2V), _p(bias), W, H, C.c_uint32(flags), _p(depth),
+                           _p(occup), _p(tie), _p(stats))
+    keys = ('culled', 'clipped', 'rasterised', 'candidates', 'covered')
+    return occup, depth, tie, dict(zip(keys, stats.tolist()))
+
+
+def face_setup(verts, W2V, W, H, flags=CULLING | CLIPPING):
+    verts = _f(verts).reshape(-1, 9)
+    out = np.zeros((len(verts), 16), dtype=np.float32)
+    bbox = np.zeros((len(verts), 4), dtype=np.int32)
+    lib().orc_face_setup(_p(verts), C.c_int64(len(verts)), _p(_f(W2V).reshape(16)), W, H, C.c_uint32(flags), _p(out), _p(bbox))
+    return out, bbox
+
+
+def render_color(verts, norms, coors, occup, W2V, V2W, W, H, flags, material, lighting, image, bias=(0.5, 0.5),
+                 parallel=True):
+    """Shades pixels with occup != -1 into `image` ([W,H,3] f32, modified in place and returned).
+    `material` is a taichi_three_b200 material node graph, `lighting` a taichi_three_b200.Lighting."""
+    from taichi_three_b200 import _lib as P
+    from taichi_three_b200.material import flatten_material
+    brdf, amb, emi, textures = flatten_material(material)
+    m = P.TinaMaterial()
+    m.n_brdf, m.n_ambient, m.n_emission, m.ntex = len(brdf), len(amb), len(emi), len(textures)
+    for i, (op, arg, c) in enumerate(brdf + amb + emi):
+        m.code[i].op, m.code[i].arg = op, arg
+        m.code[i].c[0], m.code[i].c[1], m.code[i].c[2] = c
+    tex_arrays = [np.ascontiguousarray(t.image, dtype=np.float32) for t in textures]
+    texptrs = (C.c_void_p * max(1, len(tex_arrays)))()
+    for i, t in enumerate(tex_arrays):
+        texptrs[i] = t.ctypes.data
+        m.tex_w[i], m.tex_h[i], m.tex_c[i] = t.shape
+    L = lighting.struct()
+    verts = _f(verts).reshape(-1, 9)
+    norms = _f(norms).reshape(-1, 9) if norms is not None else None
+    coors = _f(coors).reshape(-1, 6) if coors is not None else None
+    occup = np.ascontiguousarray(occup, dtype=np.int32)
+    assert image.dtype == np.float32 and image.flags['C_CONTIGUOUS'] and image.shape == (W, H, 3)
+    lib().orc_render_color(_p(verts), _p(norms), _p(coors), _p(occup), _p(_f(W2V).reshape(16)), _p(_f(V2W).reshape(16)),
+                           _p(_f(bias)), W, H, C.c_uint32(flags), C.byref(m), texptrs, C.byref(L), _p(image),
+                           1 if parallel else 0)
+    return image
+
+
+def tonemap(image):
+    out = np.ascontiguousarray(image, dtype=np.float32).copy()
+    lib().orc_tonemap(_p(out), C.c_int64(out.size))
+    return out
+
+
+# ---- mesh providers (set_object side) ---------------------------------------------------
+def grid_normals(pos):
+    pos = _f(pos)
+    nx, ny = pos.shape[:2]
+    nrm = np.empty_like(pos)
+    lib().orc_grid_normals(_p(pos), nx, ny, _p(nrm))
+    return nrm
+
+
+def grid_faces(prop):
+    prop = _f(prop)
+    nx, ny, dim = prop.shape
+    out = np.empty((2 * (nx - 1) * (ny - 1), 3, dim), dtype=np.float32)
+    lib().orc_grid_faces(_p(prop), nx, ny, dim, _p(out))
+    return out
+
+
+def grid_positions(nx, ny):
+    """mesh/grid.py:17-21 in f32."""
+    u = (np.arange(nx, dtype=np.float32) / np.float32(nx - 1))[:, None] * np.ones((1, ny), np.float32)
+    v = np.ones((nx, 1), np.float32) * (np.arange(ny, dtype=np.float32) / np.float32(ny - 1))[None, :]
+    pos = np.stack([u * np.float32(2) - np.float32(1), v * np.float32(2) - np.float32(1), np.zeros_like(u)], axis=2)
+    return np.ascontiguousarray(pos, dtype=np.float32), np.ascontiguousarray(np.stack([u, v], axis=2), dtype=np.float32)
+
+
+def transform(verts, norms, trans):
+    """mesh/trans.py:23-40 on [N,3,3] arrays."""
+    trans = np.asarray(trans, dtype=np.float64)
+    t32 = _f(trans).reshape(16)
+    tn = _f(np.transpose(np.linalg.inv(trans))[:3, :3]).reshape(9)
+    verts = _f(verts).copy()
+    lib().orc_transform_verts(_p(verts), C.c_int64(verts.size // 3), _p(t32))
+    if norms is not None:
+        norms = _f(norms).copy()
+        lib().orc_transform_norms(_p(norms), C.c_int64(norms.size // 3), _p(tn))
+    return verts, norms
+
+
+def no_culling(verts, norms=None, coors=None):
+    """mesh/cull.py:31-57: [N,...] -> [2N,...], odd copies reversed, normals negated."""
+    def dup(a, negate=False):
+        if a is None:
+            return None
+        out = np.repeat(a, 2, axis=0)
+        out[1::2] = out[1::2][:, ::-1]
+        if negate:
+            out[1::2] = -out[1::2]
+        return np.ascontiguousarray(out)
+    return dup(verts), dup(norms, True), dup(coors)
+
+
+def indexed(obj):
+    """mesh/model.py:56-73: dict {'v','vt','vn','f'} -> ([N,3,3] verts, norms, [N,3,2] coors)."""
+    f = np.asarray(obj['f'])
+    if f.ndim == 2:
+        f = np.stack([f, f, f], axis=2)
+    f = f.astype(np.int64)
+    v = _f(obj['v'])[f[:, :, 0]]
+    vt = _f(obj['vt'])[:, :2][f[:, :, 1]] if 'vt' in obj else None
+    vn = _f(obj['vn'])[f[:, :, 2]] if 'vn' in obj else None
+    return np.ascontiguousarray(v), (np.ascontiguousarray(vn) if vn is not None else None), \
+        (np.ascontiguousarray(vt) if vt is not None else None)
+
+
+def render_scene(objects, W, H, view, proj, lighting, flags, bgcolor=0.0, do_tonemap=True, bias=(0.5, 0.5)):
+    """scene/raster.py:168-207 for a list of (verts, norms, coors, material).
+    -> dict(image, pre_tonemap, depth, occups=[...], ties=[...])"""
+    W2V64 = np.asarray(proj, dtype=np.float64) @ np.asarray(view, dtype=np.float64)
+    W2V, V2W = W2V64.astype(np.float32), np.linalg.inv(W2V64).astype(np.float32)
+    image = np.empty((W, H, 3), dtype=np.float32)
+    image[...] = np.broadcast_to(np.asarray(bgcolor, dtype=np.float32), (3,))
+    depth = clear_depth(W, H)
+    occups, ties = [], []
+    for verts, norms, coors, material in objects:
+        occup, depth, tie, _ = render_occup(verts, W2V, W, H, flags, bias, depth)
+        render_color(verts, norms, coors, occup, W2V, V2W, W, H, flags, material, lighting, image, bias)
+        occups.append(occup)
+        ties.append(tie)
+    pre = image.copy()
+    if do_tonemap:
+        image = tonemap(image)
+    return dict(image=image, pre_tonemap=pre, depth=depth, occups=occups, ties=ties, W2V=W2V, V2W=V2W)

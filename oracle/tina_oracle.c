@@ -1,0 +1,506 @@
+/*
+ * tina_oracle.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * CPU restatement (plain C, IEEE f32, no contraction) of the reference's
+ * triangle-raster path, used ONLY by tests/, __graft_entry__.smoke() and
+ * bench.py's cpu_baseline / --impl reference legs as the checker / CPU baseline.
+ * The product path (taichi_three_b200/) never imports or links this file.
+ *
+ * Parity pin: the reference (taichi-dev/taichi_three) ships no golden outputs and
+ * its runtime dependency `taichi` (unpinned, setup.py:23; needs the 0.7.x API) is
+ * not installable here.  This restatement is pinned against the reference's OWN
+ * Python source executed under an f32 NumPy emulation of the Taichi runtime
+ * (oracle/ref_shim + tests/golden/make_golden.py -> tests/golden/*.npz).  Against a
+ * real Taichi JIT build parity remains unpinned.
+ *
+ * Build: gcc -O2 -ffp-contract=off -fno-fast-math -fopenmp -shared -fPIC (oracle/Makefile)
+ *
+ * Every function cites the reference file:line (relative to /root/reference) it restates.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../include/tina_b200.h"
+
+#define MAXDEPTH_F 1073741824.0f /* engine.py:12  maxdepth = 2**30 */
+
+/* x86 cvttss2si semantics of Taichi's CPU backend for int(float): NaN / out of
+ * range -> INT_MIN (SURVEY hard part 6). */
+static int32_t f2i(float x) {
+    if (!(x >= -2147483648.0f && x < 2147483648.0f)) return INT32_MIN;
+    return (int32_t)x;
+}
+/* common.py:130-137 */
+static int32_t ifloor_(float x) { return f2i(floorf(x)); }
+static int32_t iceil_(float x) { return f2i(ceilf(x)); }
+
+/* common.py:169-177  mapply(mat, pos, wei) -> (res, rew) */
+static void mapply(const float *M, const float *p, float w, float *r, float *rw) {
+    for (int i = 0; i < 3; i++) r[i] = M[i * 4 + 3] * w;
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) r[i] += M[i * 4 + j] * p[j];
+    float rew = M[15] * w;
+    for (int i = 0; i < 3; i++) rew += M[12 + i] * p[i];
+    *rw = rew;
+}
+/* common.py:181-183 */
+static void mapply_pos(const float *M, const float *p, float *r) {
+    float rw;
+    mapply(M, p, 1.0f, r, &rw);
+    for (int i = 0; i < 3; i++) r[i] = r[i] / rw;
+}
+
+static float dot3(const float *a, const float *b) { return (a[0] * b[0] + a[1] * b[1]) + a[2] * b[2]; }
+static void cross3(const float *a, const float *b, float *r) {
+    r[0] = a[1] * b[2] - a[2] * b[1];
+    r[1] = a[2] * b[0] - a[0] * b[2];
+    r[2] = a[0] * b[1] - a[1] * b[0];
+}
+/* taichi Matrix.normalized(): invlen = 1 / sqrt(norm_sqr); invlen * v */
+static void normalize3(float *v) {
+    float inv = 1.0f / sqrtf(dot3(v, v));
+    for (int i = 0; i < 3; i++) v[i] = inv * v[i];
+}
+
+typedef struct {
+    int ok;              /* passed cull + clip */
+    int culled, clipped;
+    float Avz, Bvz, Cvz; /* NDC z */
+    float b[2], c[2], bcn[2], can[2], wsc[3];
+    int32_t bot[2], top[2];
+} FaceSetup;
+
+/* triangle.py:93-113 */
+static void face_setup(const float *V9, const float *W2V, int W, int H, uint32_t flags, FaceSetup *s) {
+    float Av[3], Bv[3], Cv[3], rw[3], tmp[3];
+    const float *Al = V9, *Bl = V9 + 3, *Cl = V9 + 6;
+    mapply(W2V, Al, 1.0f, tmp, &rw[0]);
+    for (int i = 0; i < 3; i++) Av[i] = tmp[i] / rw[0];
+    mapply(W2V, Bl, 1.0f, tmp, &rw[1]);
+    for (int i = 0; i < 3; i++) Bv[i] = tmp[i] / rw[1];
+    mapply(W2V, Cl, 1.0f, tmp, &rw[2]);
+    for (int i = 0; i < 3; i++) Cv[i] = tmp[i] / rw[2];
+    s->ok = 0;
+    s->culled = s->clipped = 0;
+    /* triangle.py:95-98 */
+    float facing = (Bv[0] - Av[0]) * (Cv[1] - Av[1]) - (Bv[1] - Av[1]) * (Cv[0] - Av[0]);
+    if (facing <= 0 && (flags & TINA_CULLING)) {
+        s->culled = 1;
+        return;
+    }
+    /* triangle.py:100-104 */
+    if (flags & TINA_CLIPPING) {
+        int ina = 1, inb = 1, inc = 1;
+        for (int i = 0; i < 3; i++) {
+            ina &= (-1.0f <= Av[i]) && (Av[i] <= 1.0f);
+            inb &= (-1.0f <= Bv[i]) && (Bv[i] <= 1.0f);
+            inc &= (-1.0f <= Cv[i]) && (Cv[i] <= 1.0f);
+        }
+        if (!ina && !inb && !inc) {
+            s->clipped = 1;
+            return;
+        }
+    }
+    /* engine.py:60-61 */
+    float res[2] = {(float)W, (float)H};
+    float a[2], b[2], c[2];
+    for (int i = 0; i < 2; i++) {
+        a[i] = (Av[i] * 0.5f + 0.5f) * res[i];
+        b[i] = (Bv[i] * 0.5f + 0.5f) * res[i];
+        c[i] = (Cv[i] * 0.5f + 0.5f) * res[i];
+    }
+    /* triangle.py:108-109 */
+    int resi[2] = {W, H};
+    for (int i = 0; i < 2; i++) {
+        int32_t bot = ifloor_(fminf(fminf(a[i], b[i]), c[i]));
+        int32_t top = iceil_(fmaxf(fmaxf(a[i], b[i]), c[i]));
+        s->bot[i] = bot > 0 ? bot : 0;
+        s->top[i] = top < resi[i] - 1 ? top : resi[i] - 1;
+    }
+    /* triangle.py:110-113 */
+    float n = (b[0] - a[0]) * (c[1] - a[1]) - (b[1] - a[1]) * (c[0] - a[0]);
+    for (int i = 0; i < 2; i++) {
+        s->bcn[i] = (b[i] - c[i]) / n;
+        s->can[i] = (c[i] - a[i]) / n;
+        s->b[i] = b[i];
+        s->c[i] = c[i];
+    }
+    for (int i = 0; i < 3; i++) s->wsc[i] = 1.0f / rw[i];
+    s->Avz = Av[2];
+    s->Bvz = Bv[2];
+    s->Cvz = Cv[2];
+    s->ok = 1;
+}
+
+/* triangle.py:115-119 (and :147-151) */
+static void pixel_weights(const FaceSetup *s, int x, int y, const float *bias, float *wei) {
+    float px = (float)x + bias[0], py = (float)y + bias[1];
+    float w_bc = (px - s->b[0]) * s->bcn[1] - (py - s->b[1]) * s->bcn[0];
+    float w_ca = (px - s->c[0]) * s->can[1] - (py - s->c[1]) * s->can[0];
+    wei[0] = w_bc * s->wsc[0];
+    wei[1] = w_ca * s->wsc[1];
+    wei[2] = ((1.0f - w_bc) - w_ca) * s->wsc[2];
+    float sum = (wei[0] + wei[1]) + wei[2];
+    wei[0] = wei[0] / sum;
+    wei[1] = wei[1] / sum;
+    wei[2] = wei[2] / sum;
+}
+
+/*
+ * triangle.py:89-131, serial execution order (face 0..N-1): the deterministic
+ * restatement of the racy atomic_min/store pair (:123-125): lowest face id wins
+ * exact depth ties, a face only wins with depth strictly below what is stored.
+ * depth[] persists across calls (engine.py:68-70 clears it), occup[] is reset.
+ * tie[] (optional): 1 where >= 2 covering faces of this call share the winning depth.
+ * stats[] (optional): {culled, clipped, rasterised, candidate pixels, covered samples}
+ */
+void orc_render_occup(const float *verts, int64_t nfaces, const float *W2V, const float *bias, int W, int H,
+                      uint32_t flags, int32_t *depth, int32_t *occup, uint8_t *tie, int64_t *stats) {
+    int64_t npix = (int64_t)W * H;
+    for (int64_t i = 0; i < npix; i++) occup[i] = -1; /* triangle.py:90-91 */
+    if (tie) memset(tie, 0, npix);
+    int64_t st[5] = {0, 0, 0, 0, 0};
+    for (int64_t f = 0; f < nfaces; f++) {
+        FaceSetup s;
+        face_setup(verts + f * 9, W2V, W, H, flags, &s);
+        if (!s.ok) {
+            st[0] += s.culled;
+            st[1] += s.clipped;
+            continue;
+        }
+        st[2]++;
+        for (int32_t x = s.bot[0]; x <= s.top[0]; x++)
+            for (int32_t y = s.bot[1]; y <= s.top[1]; y++) {
+                float wei[3];
+                st[3]++;
+                pixel_weights(&s, x, y, bias, wei);
+                if (!(wei[0] >= 0 && wei[1] >= 0 && wei[2] >= 0)) continue; /* :120 */
+                st[4]++;
+                float depth_f = (wei[0] * s.Avz + wei[1] * s.Bvz) + wei[2] * s.Cvz; /* :121 */
+                int32_t d = f2i(depth_f * MAXDEPTH_F);                             /* :122 */
+                int64_t P = (int64_t)x * H + y;
+                int32_t old = depth[P];
+                if (old > d) { /* :123-125 */
+                    depth[P] = d;
+                    occup[P] = (int32_t)f;
+                    if (tie) tie[P] = 0;
+                } else if (tie && old == d && occup[P] != -1) {
+                    tie[P] = 1;
+                }
+            }
+    }
+    if (stats) memcpy(stats, st, sizeof st);
+}
+
+/* Per-face setup record export (tests compare the CUDA setup kernel against it):
+ * out[f*16 ..] = ok, bcn.xy, can.xy, b.xy, c.xy, wsc.xyz, z.xyz ; bbox[f*4..] = bot.xy, top.xy */
+void orc_face_setup(const float *verts, int64_t nfaces, const float *W2V, int W, int H, uint32_t flags, float *out,
+                    int32_t *bbox) {
+    for (int64_t f = 0; f < nfaces; f++) {
+        FaceSetup s;
+        memset(&s, 0, sizeof s);
+        face_setup(verts + f * 9, W2V, W, H, flags, &s);
+        float *o = out + f * 16;
+        o[0] = (float)s.ok;
+        o[1] = s.bcn[0], o[2] = s.bcn[1], o[3] = s.can[0], o[4] = s.can[1];
+        o[5] = s.b[0], o[6] = s.b[1], o[7] = s.c[0], o[8] = s.c[1];
+        o[9] = s.wsc[0], o[10] = s.wsc[1], o[11] = s.wsc[2];
+        o[12] = s.Avz, o[13] = s.Bvz, o[14] = s.Cvz, o[15] = 0;
+        bbox[f * 4 + 0] = s.bot[0], bbox[f * 4 + 1] = s.bot[1];
+        bbox[f * 4 + 2] = s.top[0], bbox[f * 4 + 3] = s.top[1];
+    }
+}
+
+/*
+ * The reference's parallel structure for TIMING ONLY (cpu_baseline): faces across
+ * threads, atomic min on depth, racy occup store (triangle.py:92,123-125 on the
+ * Taichi CPU backend = one task per face range on a thread pool).
+ */
+void orc_render_occup_parallel(const float *verts, int64_t nfaces, const float *W2V, const float *bias, int W, int H,
+                               uint32_t flags, int32_t *depth, int32_t *occup) {
+    int64_t npix = (int64_t)W * H;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < npix; i++) occup[i] = -1;
+#pragma omp parallel for schedule(dynamic, 1024)
+    for (int64_t f = 0; f < nfaces; f++) {
+        FaceSetup s;
+        face_setup(verts + f * 9, W2V, W, H, flags, &s);
+        if (!s.ok) continue;
+        for (int32_t x = s.bot[0]; x <= s.top[0]; x++)
+            for (int32_t y = s.bot[1]; y <= s.top[1]; y++) {
+                float wei[3];
+                pixel_weights(&s, x, y, bias, wei);
+                if (!(wei[0] >= 0 && wei[1] >= 0 && wei[2] >= 0)) continue;
+                float depth_f = (wei[0] * s.Avz + wei[1] * s.Bvz) + wei[2] * s.Cvz;
+                int32_t d = f2i(depth_f * MAXDEPTH_F);
+                int64_t P = (int64_t)x * H + y;
+                int32_t old = __atomic_load_n(&depth[P], __ATOMIC_RELAXED);
+                while (old > d && !__atomic_compare_exchange_n(&depth[P], &old, d, 1, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {
+                }
+                if (old > d)
+                    if (__atomic_load_n(&depth[P], __ATOMIC_RELAXED) >= d) occup[P] = (int32_t)f;
+            }
+    }
+}
+
+/* ---- materials ---------------------------------------------------------------- */
+
+typedef struct {
+    float pos[3], color[3], normal[3], texcoord[3];
+} ShadeInputs;
+
+/* common.py:140-149 bilerp + nodes.py:107-111 Texture.__call__; the `+1` texel index
+ * is clamped to the last texel (reference reads one past the end with weight 0, Appendix B) */
+static void tex_sample(const float *tex, int w, int h, int c, const float *uv, float *out) {
+    float p[2] = {uv[0] * (float)(w - 1), uv[1] * (float)(h - 1)};
+    int32_t I[2] = {ifloor_(p[0]), ifloor_(p[1])};
+    float x[2] = {p[0] - (float)I[0], p[1] - (float)I[1]};
+    float y[2] = {1.0f - x[0], 1.0f - x[1]};
+    int i0 = I[0] < 0 ? 0 : (I[0] > w - 1 ? w - 1 : I[0]);
+    int j0 = I[1] < 0 ? 0 : (I[1] > h - 1 ? h - 1 : I[1]);
+    int i1 = I[0] + 1 < 0 ? 0 : (I[0] + 1 > w - 1 ? w - 1 : I[0] + 1);
+    int j1 = I[1] + 1 < 0 ? 0 : (I[1] + 1 > h - 1 ? h - 1 : I[1] + 1);
+    for (int k = 0; k < 3; k++) {
+        int kk = c == 1 ? 0 : k;
+        float f11 = tex[((int64_t)i1 * h + j1) * c + kk];
+        float f10 = tex[((int64_t)i1 * h + j0) * c + kk];
+        float f00 = tex[((int64_t)i0 * h + j0) * c + kk];
+        float f01 = tex[((int64_t)i0 * h + j1) * c + kk];
+        out[k] = ((f11 * x[0] * x[1] + f10 * x[0] * y[1]) + f00 * y[0] * y[1]) + f01 * y[0] * x[1];
+    }
+}
+
+#define STK 16
+/* evaluate one postfix program; see include/tina_b200.h for the op table */
+static void run_program(const TinaMaterial *m, const float *const *texhost, int begin, int n, const ShadeInputs *in,
+                        const float *nrm, const float *idir, const float *odir, float *out) {
+    float st[STK][3];
+    int sp = 0;
+    for (int pc = begin; pc < begin + n; pc++) {
+        const TinaInstr *I = &m->code[pc];
+        switch (I->op) {
+        case TINA_OP_CONST:
+            for (int k = 0; k < 3; k++) st[sp][k] = I->c[k];
+            sp++;
+            break;
+        case TINA_OP_INPUT: {
+            const float *src = I->arg == 0 ? in->pos : I->arg == 1 ? in->color : I->arg == 2 ? in->normal : in->texcoord;
+            for (int k = 0; k < 3; k++) st[sp][k] = src[k];
+            sp++;
+            break;
+        }
+        case TINA_OP_TEXTURE: {
+            float uv[2] = {st[sp - 1][0], st[sp - 1][1]};
+            tex_sample(texhost[I->arg], m->tex_w[I->arg], m->tex_h[I->arg], m->tex_c[I->arg], uv, st[sp - 1]);
+            break;
+        }
+        case TINA_OP_FRESNEL: { /* material.py:69-83 */
+            float *specular = st[sp - 1], *albedo = st[sp - 2], *metallic = st[sp - 3];
+            for (int k = 0; k < 3; k++)
+                metallic[k] = metallic[k] * albedo[k] + (1.0f - metallic[k]) * 0.16f * (specular[k] * specular[k]);
+            sp -= 2;
+            break;
+        }
+        case TINA_OP_LAMBERT: { /* material.py:392-393 */
+            float v = (float)(1.0 / 3.14159265358979323846); /* Python folds 1 / ti.pi in f64 */
+            for (int k = 0; k < 3; k++) st[sp][k] = v;
+            sp++;
+            break;
+        }
+        case TINA_OP_PHONG: { /* material.py:450-454, common.py:197-199 */
+            float *mm = st[sp - 1];
+            float I3[3] = {-idir[0], -idir[1], -idir[2]};
+            float t = 2.0f * dot3(nrm, I3);
+            float rdir[3];
+            for (int k = 0; k < 3; k++) rdir[k] = I3[k] - t * nrm[k];
+            float VoR = fmaxf(0.0f, dot3(odir, rdir));
+            for (int k = 0; k < 3; k++) mm[k] = powf(VoR, mm[k]) * (mm[k] + 2.0f) / 2.0f;
+            break;
+        }
+        case TINA_OP_COOK: { /* material.py:323-362 */
+            float *f0 = st[sp - 1], *rough = st[sp - 2];
+            const float EPS = 1e-10f, eps = 1e-6f;
+            float half[3] = {idir[0] + odir[0], idir[1] + odir[1], idir[2] + odir[2]};
+            normalize3(half);
+            float NoH = fmaxf(EPS, dot3(half, nrm));
+            float NoL = fmaxf(EPS, dot3(idir, nrm));
+            float NoV = fmaxf(EPS, dot3(odir, nrm));
+            float VoH = fminf((float)(1 - 1e-10), fmaxf(EPS, dot3(half, odir)));
+            for (int k = 0; k < 3; k++) {
+                float alpha2 = fmaxf(eps, rough[k] * rough[k]);
+                float denom = 1.0f - (NoH * NoH) * (1.0f - alpha2);
+                float ndf = alpha2 / (denom * denom);
+                float kk = alpha2 / 2.0f;
+                float vdf = 1.0f / ((NoV * kk + 1.0f) - kk);
+                vdf *= 1.0f / ((NoL * kk + 1.0f) - kk);
+                vdf /= 1.0f * (1.0f - alpha2) + 12.566370614359172f * alpha2; /* common.py:221-223 lerp */
+                float fdf = f0[k] + (1.0f - f0[k]) * powf(1.0f - VoH, 5.0f);
+                rough[k] = fdf * vdf * ndf;
+            }
+            sp -= 1;
+            break;
+        }
+        case TINA_OP_MIX: { /* material.py:96-118 */
+            float *b = st[sp - 1], *a = st[sp - 2], *fac = st[sp - 3];
+            for (int k = 0; k < 3; k++) fac[k] = (1.0f - fac[k]) * a[k] + fac[k] * b[k];
+            sp -= 2;
+            break;
+        }
+        case TINA_OP_MUL: { /* material.py:157-176 */
+            float *wei = st[sp - 1], *fac = st[sp - 2];
+            for (int k = 0; k < 3; k++) fac[k] = fac[k] * wei[k];
+            sp -= 1;
+            break;
+        }
+        case TINA_OP_ADD: {
+            float *b = st[sp - 1], *a = st[sp - 2];
+            for (int k = 0; k < 3; k++) a[k] = a[k] + b[k];
+            sp -= 1;
+            break;
+        }
+        }
+    }
+    for (int k = 0; k < 3; k++) out[k] = sp > 0 ? st[sp - 1][k] : 0.0f;
+}
+
+/* advans.py:32-35 */
+static float aces(float c) { return c * (2.51f * c + 0.03f) / (c * (2.43f * c + 0.59f) + 0.14f); }
+
+void orc_tonemap(float *img, int64_t n) {
+    for (int64_t i = 0; i < n; i++) img[i] = aces(img[i]);
+}
+
+/*
+ * triangle.py:134-153 + :32-49 (interpolate) + shader.py:82-93,119-131 +
+ * lighting.py:84-98.  Writes image[P] for pixels with occup[P] != -1 only.
+ * `textures` are HOST pointers replacing mat->tex (which holds device pointers
+ * in the product).
+ */
+void orc_render_color(const float *verts, const float *norms, const float *coors, const int32_t *occup,
+                      const float *W2V, const float *V2W, const float *bias, int W, int H, uint32_t flags,
+                      const TinaMaterial *mat, const float *const *textures, const TinaLighting *L, float *image,
+                      int parallel) {
+#pragma omp parallel for schedule(dynamic, 64) if (parallel)
+    for (int x = 0; x < W; x++)
+        for (int y = 0; y < H; y++) {
+            int64_t P = (int64_t)x * H + y;
+            int32_t f = occup[P];
+            if (f == -1) continue;
+            const float *V9 = verts + (int64_t)f * 9;
+            FaceSetup s;
+            /* the reference re-reads bcn/can/boo/coo/wsc cached by render_occup (:140-145);
+             * recomputing them with the same ops gives the same bits */
+            face_setup(V9, W2V, W, H, 0u, &s);
+            float wei[3];
+            pixel_weights(&s, x, y, bias, wei);
+            ShadeInputs in;
+            const float *A = V9, *B = V9 + 3, *C = V9 + 6;
+            for (int k = 0; k < 3; k++) in.pos[k] = (wei[0] * A[k] + wei[1] * B[k]) + wei[2] * C[k]; /* :33 */
+            if (flags & TINA_SMOOTHING) {
+                const float *N9 = norms + (int64_t)f * 9;
+                for (int k = 0; k < 3; k++) in.normal[k] = (wei[0] * N9[k] + wei[1] * N9[3 + k]) + wei[2] * N9[6 + k];
+            } else {
+                float e1[3] = {B[0] - A[0], B[1] - A[1], B[2] - A[2]};
+                float e2[3] = {C[0] - A[0], C[1] - A[1], C[2] - A[2]};
+                cross3(e1, e2, in.normal);
+            }
+            normalize3(in.normal); /* :41 */
+            in.texcoord[0] = in.texcoord[1] = in.texcoord[2] = 0.0f;
+            if (flags & TINA_TEXTURING) {
+                const float *T6 = coors + (int64_t)f * 6;
+                for (int k = 0; k < 2; k++) in.texcoord[k] = (wei[0] * T6[k] + wei[1] * T6[2 + k]) + wei[2] * T6[4 + k];
+            }
+            in.color[0] = in.color[1] = in.color[2] = 1.0f;
+            /* shader.py:82-93 */
+            float p[2] = {(float)x + bias[0], (float)y + bias[1]};
+            float q[3] = {p[0] / (float)W * 2.0f - 1.0f, p[1] / (float)H * 2.0f - 1.0f, -1.0f};
+            float ro[3], ro1[3], rd[3];
+            mapply_pos(V2W, q, ro);
+            q[2] = 1.0f;
+            mapply_pos(V2W, q, ro1);
+            for (int k = 0; k < 3; k++) rd[k] = ro1[k] - ro[k];
+            normalize3(rd);
+            float viewdir[3] = {-rd[0], -rd[1], -rd[2]};
+            /* lighting.py:84-98 */
+            float res[3] = {0, 0, 0}, tmp[3];
+            float zero[3] = {0, 0, 0};
+            run_program(mat, textures, mat->n_brdf + mat->n_ambient, mat->n_emission, &in, zero, zero, zero, tmp);
+            for (int k = 0; k < 3; k++) res[k] += tmp[k];
+            run_program(mat, textures, mat->n_brdf, mat->n_ambient, &in, zero, zero, zero, tmp);
+            for (int k = 0; k < 3; k++) res[k] += L->ambient[k] * tmp[k];
+            for (int l = 0; l < L->nlights; l++) {
+                float ld[3];
+                for (int k = 0; k < 3; k++) ld[k] = L->dirs[l][k] - in.pos[k] * L->dirs[l][3];
+                float dist = sqrtf(dot3(ld, ld));
+                for (int k = 0; k < 3; k++) ld[k] = ld[k] / dist;
+                float cos_i = dot3(in.normal, ld);
+                if (cos_i > 0) {
+                    float d2 = dist * dist;
+                    run_program(mat, textures, 0, mat->n_brdf, &in, in.normal, ld, viewdir, tmp);
+                    for (int k = 0; k < 3; k++) res[k] += cos_i * (L->colors[l][k] / d2) * tmp[k];
+                }
+            }
+            for (int k = 0; k < 3; k++) image[P * 3 + k] = res[k];
+        }
+}
+
+/* ---- mesh providers feeding set_object ------------------------------------------ */
+
+/* mesh/grid.py:26-35 MeshGrid.pre_compute; pos, nrm: [nx][ny][3] */
+void orc_grid_normals(const float *pos, int nx, int ny, float *nrm) {
+    for (int i = 0; i < nx; i++)
+        for (int j = 0; j < ny; j++) {
+            int i2 = i - 1 > 0 ? i - 1 : 0, j2 = j - 1 > 0 ? j - 1 : 0;
+            int i1 = i + 1 < nx - 1 ? i + 1 : nx - 1, j1 = j + 1 < ny - 1 ? j + 1 : ny - 1;
+            float dx[3], dy[3];
+            for (int k = 0; k < 3; k++) {
+                dy[k] = pos[((int64_t)i * ny + j1) * 3 + k] - pos[((int64_t)i * ny + j2) * 3 + k];
+                dx[k] = pos[((int64_t)i1 * ny + j) * 3 + k] - pos[((int64_t)i2 * ny + j) * 3 + k];
+            }
+            float *o = nrm + ((int64_t)i * ny + j) * 3;
+            cross3(dx, dy, o);
+            normalize3(o);
+        }
+}
+
+/* mesh/grid.py:45-58 _get_face_props for a [nx][ny][dim] property -> out[nfaces][3][dim] */
+void orc_grid_faces(const float *prop, int nx, int ny, int dim, float *out) {
+    int64_t nfaces = 2 * (int64_t)(nx - 1) * (ny - 1);
+    int stride = nx - 1; /* sic: res.x - 1 for both div and mod (grid.py:46) */
+    for (int64_t n = 0; n < nfaces; n++) {
+        int64_t m = n / 2;
+        int i = (int)(m / stride), j = (int)(m % stride);
+        const float *a = prop + ((int64_t)i * ny + j) * dim, *b = prop + ((int64_t)(i + 1) * ny + j) * dim;
+        const float *c = prop + ((int64_t)(i + 1) * ny + j + 1) * dim, *d = prop + ((int64_t)i * ny + j + 1) * dim;
+        const float *src[3] = {a, b, c};
+        if (n % 2 != 0) src[1] = c, src[2] = d;
+        for (int k = 0; k < 3; k++) memcpy(out + (n * 3 + k) * dim, src[k], sizeof(float) * dim);
+    }
+}
+
+/* mesh/trans.py:28-40 applied to [n][3] arrays; trans 4x4, trans_normal 3x3 row-major */
+void orc_transform_verts(float *v, int64_t n, const float *trans) {
+    for (int64_t i = 0; i < n; i++) {
+        float r[3];
+        mapply_pos(trans, v + i * 3, r);
+        memcpy(v + i * 3, r, sizeof r);
+    }
+}
+void orc_transform_norms(float *v, int64_t n, const float *tn) {
+    for (int64_t i = 0; i < n; i++) {
+        float *p = v + i * 3, r[3];
+        for (int a = 0; a < 3; a++) r[a] = (tn[a * 3 + 0] * p[0] + tn[a * 3 + 1] * p[1]) + tn[a * 3 + 2] * p[2];
+        memcpy(p, r, sizeof r);
+    }
+}
+
+int orc_num_threads(void) {
+#ifdef _OPENMP
+    extern int omp_get_max_threads(void);
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}

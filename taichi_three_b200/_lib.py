@@ -1,0 +1,101 @@
+"""ctypes binding of the C ABI in include/tina_b200.h (libtina_b200.so).
+
+There is NO fallback: if the CUDA library is missing or a call fails this raises.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'csrc', 'libtina_b200.so')
+
+TINA_SMOOTHING, TINA_TEXTURING, TINA_CULLING, TINA_CLIPPING = 1, 2, 4, 8
+TINA_COLOR_TONEMAP, TINA_COLOR_FILL_BG = 1, 2
+TINA_MAX_LIGHTS, TINA_MAX_INSTR, TINA_MAX_TEX = 16, 96, 4
+
+(OP_CONST, OP_INPUT, OP_TEXTURE, OP_FRESNEL, OP_LAMBERT, OP_PHONG, OP_COOK, OP_MIX, OP_MUL,
+ OP_ADD) = range(10)
+
+
+class TinaLighting(C.Structure):
+    _fields_ = [('dirs', (C.c_float * 4) * TINA_MAX_LIGHTS),
+                ('colors', (C.c_float * 4) * TINA_MAX_LIGHTS),
+                ('ambient', C.c_float * 4),
+                ('nlights', C.c_int32),
+                ('pad', C.c_int32 * 3)]
+
+
+class TinaInstr(C.Structure):
+    _fields_ = [('op', C.c_int32), ('arg', C.c_int32), ('c', C.c_float * 3)]
+
+
+class TinaMaterial(C.Structure):
+    _fields_ = [('n_brdf', C.c_int32), ('n_ambient', C.c_int32), ('n_emission', C.c_int32), ('ntex', C.c_int32),
+                ('tex', C.c_void_p * TINA_MAX_TEX),
+                ('tex_w', C.c_int32 * TINA_MAX_TEX), ('tex_h', C.c_int32 * TINA_MAX_TEX),
+                ('tex_c', C.c_int32 * TINA_MAX_TEX),
+                ('code', TinaInstr * TINA_MAX_INSTR)]
+
+
+# name -> (restype, argtypes); every symbol include/tina_b200.h declares
+_vp, _i, _i64, _u32, _f = C.c_void_p, C.c_int, C.c_int64, C.c_uint32, C.c_float
+_fp = C.POINTER(C.c_float)
+SIGNATURES = {
+    'tina_last_error': (C.c_char_p, []),
+    'tina_version': (_i, []),
+    'tina_engine_create': (_i, [C.POINTER(_vp), _i, _i, _i]),
+    'tina_engine_destroy': (_i, [_vp]),
+    'tina_engine_set_camera': (_i, [_vp, _fp, _fp]),
+    'tina_engine_set_bias': (_i, [_vp, _f, _f]),
+    'tina_engine_clear_depth': (_i, [_vp, _vp]),
+    'tina_engine_keys': (_i, [_vp, C.POINTER(_vp)]),
+    'tina_engine_depth': (_i, [_vp, _vp, _vp]),
+    'tina_engine_set_face_base': (_i, [_vp, _u32]),
+    'tina_engine_get_face_base': (_i, [_vp, C.POINTER(_u32)]),
+    'tina_raster_create': (_i, [C.POINTER(_vp), _vp, _i64, _u32]),
+    'tina_raster_destroy': (_i, [_vp]),
+    'tina_raster_set_faces': (_i, [_vp, _vp, _vp, _vp, _i64, _i, _vp]),
+    'tina_raster_set_faces_indexed': (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _fp, _fp, _u32, _vp]),
+    'tina_raster_set_faces_grid': (_i, [_vp, _vp, _i, _i, _fp, _fp, _u32, _vp]),
+    'tina_raster_render_occup': (_i, [_vp, _vp]),
+    'tina_raster_render_color': (_i, [_vp, C.POINTER(TinaMaterial), C.POINTER(TinaLighting), _vp, _u32, _fp, _vp]),
+    'tina_raster_occup': (_i, [_vp, _vp, _vp]),
+    'tina_raster_buffers': (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i64)]),
+    'tina_raster_set_tuning': (_i, [_vp, _i, _i]),
+    'tina_raster_stats': (_i, [_vp, C.POINTER(_i64)]),
+    'tina_image_fill': (_i, [_vp, _i64, _fp, _vp]),
+    'tina_image_tonemap': (_i, [_vp, _i64, _vp]),
+}
+
+_lib = None
+
+
+class TinaError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load libtina_b200.so (built in-tree by __graft_entry__.build()); raise if absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f'{LIB_PATH} not found: build it with `python -c "import __graft_entry__ as g; g.build()"` '
+                '(nvcc, sm_100a). taichi_three_b200 has no CPU fallback.')
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = l
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise TinaError(f'libtina_b200 error {rc}: {lib().tina_last_error().decode()}')
+
+
+def f32_array(values, n):
+    import numpy as np
+    a = np.ascontiguousarray(np.asarray(values, dtype=np.float32).reshape(-1))
+    assert a.size == n, (a.size, n)
+    return a, a.ctypes.data_as(_fp)

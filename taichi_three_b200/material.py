@@ -1,0 +1,317 @@
+"""Material node graph (reference tina/matr/nodes.py, tina/matr/material.py).
+
+The reference binds these nodes at Taichi-JIT time; here the same Python-facing classes are
+*flattened on the host* into the postfix program of include/tina_b200.h (TinaMaterial)
+which the deferred shading kernel interprets.  Nodes outside the rasteriser's subset
+(path-tracing `sample*`, IBL, Glass/Mirror/volumes, LambdaNode, procedural textures) raise
+NotImplementedError instead of silently rendering something else.
+"""
+import numpy as np
+
+from . import _lib
+
+
+class Node:
+    arguments = []
+    defaults = []
+
+    def __init__(self, **kwargs):
+        # nodes.py:9-33: defaults, literal -> Const, str -> Texture (image path) or Input
+        self.params = {}
+        for dfl, key in zip(self.defaults, self.arguments):
+            if key in kwargs:
+                value = kwargs.pop(key)
+            else:
+                if dfl is None:
+                    raise ValueError(f'`{key}` must specified for `{type(self)}`')
+                value = dfl
+            self.params[key] = as_node(value)
+        for key in kwargs:
+            raise TypeError(f"{type(self).__name__}() got an unexpected keyword argument '{key}', "
+                            f"supported keywords are: {self.arguments}")
+
+    def param(self, key):
+        return self.params[key]
+
+
+def as_node(value):
+    if isinstance(value, Node):
+        return value
+    if isinstance(value, (int, float, np.integer, np.floating)):
+        return Const(value)
+    if isinstance(value, (list, tuple, np.ndarray)):
+        return Const(np.asarray(value, dtype=np.float64))
+    if isinstance(value, str):
+        if any(value.endswith(x) for x in ('.png', '.jpg', '.bmp')):
+            return Texture(value)
+        return Input(value)
+    raise TypeError(f'cannot use {value!r} as a material parameter')
+
+
+class Const(Node):
+    def __init__(self, value):  # nodes.py:42-49
+        self.value = value
+
+
+class Param(Node):
+    """0-d runtime parameter (nodes.py:52-76); its current value is read at every render."""
+
+    def __init__(self, dtype=float, dim=None, initial=0):
+        self._value = np.zeros(dim if dim is not None else (), dtype=np.float64)
+        self._value[...] = initial
+        self.initial = initial
+        self.value = self
+
+    def __getitem__(self, idx):
+        return self._value.copy() if self._value.ndim else float(self._value)
+
+    def __setitem__(self, idx, v):
+        self._value[...] = v
+
+    def make_slider(self, gui, title, min=0, max=1, step=0.01):
+        self.slider = gui.slider(title, min, max, step)
+        self.slider.value = self.initial
+
+        @gui.post_show
+        def post_show(gui):
+            self._value[...] = self.slider.value
+
+
+class Input(Node):
+    NAMES = {'pos': 0, 'color': 1, 'normal': 2, 'texcoord': 3}
+
+    def __init__(self, name):  # nodes.py:79-96
+        if name not in self.NAMES:
+            raise ValueError(f'unknown shader input {name!r} (have {list(self.NAMES)})')
+        self.name = name
+
+
+class Texture(Node):
+    arguments = ['texcoord']
+    defaults = ['texcoord']
+
+    def __init__(self, path, **kwargs):  # nodes.py:99-111 + advans.py:8-28 texture_as_field
+        if isinstance(path, str):
+            from PIL import Image
+            # ti.imread convention: [x][y] with y up
+            img = np.array(Image.open(path))
+            img = np.swapaxes(img, 0, 1)[:, ::-1]
+        else:
+            img = np.array(path)
+        if img.dtype == np.uint8:
+            img = np.float32(img / 255)
+        img = np.ascontiguousarray(img, dtype=np.float32)
+        if img.ndim == 2:
+            img = img[:, :, None]
+        if img.ndim != 3 or img.shape[2] not in (1, 3, 4):
+            raise ValueError(f'unsupported texture shape {img.shape}')
+        if img.shape[2] == 4:  # colour math in the reference is vec3; keep RGB
+            img = np.ascontiguousarray(img[:, :, :3])
+        self.image = img
+        self._device = None
+        super().__init__(**kwargs)
+
+    def device_tensor(self, device):
+        import torch
+        if self._device is None or self._device.device != device:
+            self._device = torch.as_tensor(self.image).to(device).contiguous()
+        return self._device
+
+
+class FresnelFactor(Node):  # material.py:69-83
+    arguments = ['metallic', 'albedo', 'specular']
+    defaults = [0.0, 1.0, 0.5]
+
+
+class IMaterial(Node):  # material.py:5-57 (brdf / ambient / emission only)
+    def __add__(self, other):
+        return AddMaterial(self, other)
+
+    def mix(self, other, factor):
+        return MixMaterial(self, other, factor)
+
+    def __mul__(self, factor):
+        return ScaleMaterial(self, factor)
+
+    __rmul__ = __mul__
+
+
+class MixMaterial(IMaterial):  # material.py:91-118
+    arguments = ['factor']
+    defaults = [0.5]
+
+    def __init__(self, mat1, mat2, factor):
+        super().__init__(factor=factor)
+        self.mat1, self.mat2 = mat1, mat2
+
+
+class ScaleMaterial(IMaterial):  # material.py:152-176
+    arguments = ['factor']
+    defaults = [1.0]
+
+    def __init__(self, mat, factor):
+        super().__init__(factor=factor)
+        self.mat = mat
+
+
+class AddMaterial(IMaterial):  # material.py:199-220
+    def __init__(self, mat1, mat2):
+        super().__init__()
+        self.mat1, self.mat2 = mat1, mat2
+
+
+class Lambert(IMaterial):  # material.py:387-396
+    pass
+
+
+class Phong(IMaterial):  # material.py:445-457
+    arguments = ['shineness']
+    defaults = [32.0]
+
+
+class CookTorrance(IMaterial):  # material.py:243-362
+    arguments = ['roughness', 'fresnel']
+    defaults = [0.4, 1.0]
+
+
+class Emission(IMaterial):  # material.py:659-676
+    pass
+
+
+def Classic(color='color', shineness=32, specular=0.4):  # material.py:684-688
+    return MixMaterial(Lambert() * color, Phong(shineness=shineness), specular)
+
+
+def Diffuse(color='color'):  # material.py:691-693
+    return Lambert() * color
+
+
+def Lamp(color='color'):  # material.py:696-698
+    return Emission() * color
+
+
+def PBR(basecolor='color', metallic=0.0, roughness=0.4, specular=0.5):  # material.py:701-706
+    mat_diff = Lambert() * basecolor
+    f0 = FresnelFactor(metallic=metallic, albedo=basecolor, specular=specular)
+    mat_spec = CookTorrance(roughness=roughness, fresnel=f0)
+    return MixMaterial(mat_diff, mat_spec, f0)
+
+
+# ---------------------------------------------------------------------------------------
+# flattening
+# ---------------------------------------------------------------------------------------
+class _Program:
+    def __init__(self):
+        self.code = []
+        self.textures = []
+
+    def emit(self, op, arg=0, c=(0.0, 0.0, 0.0)):
+        self.code.append((op, int(arg), tuple(float(x) for x in c)))
+
+    def const(self, v):
+        a = np.asarray(v, dtype=np.float64).reshape(-1)
+        if a.size == 1:
+            a = np.repeat(a, 3)
+        if a.size == 2:
+            a = np.append(a, 0.0)
+        if a.size != 3:
+            raise ValueError(f'material constants must be scalars or 3-vectors, got {v!r}')
+        self.emit(_lib.OP_CONST, 0, a)
+
+    def tex_index(self, node):
+        for i, t in enumerate(self.textures):
+            if t is node:
+                return i
+        if len(self.textures) >= _lib.TINA_MAX_TEX:
+            raise NotImplementedError(f'at most {_lib.TINA_MAX_TEX} textures per material')
+        self.textures.append(node)
+        return len(self.textures) - 1
+
+
+def _emit_value(P, node):
+    """Parameter nodes (evaluate to a value)."""
+    if isinstance(node, Param):
+        P.const(node[None])
+    elif isinstance(node, Const):
+        P.const(node.value)
+    elif isinstance(node, Input):
+        P.emit(_lib.OP_INPUT, Input.NAMES[node.name])
+    elif isinstance(node, Texture):
+        _emit_value(P, node.param('texcoord'))
+        P.emit(_lib.OP_TEXTURE, P.tex_index(node))
+    elif isinstance(node, FresnelFactor):
+        for key in ('metallic', 'albedo', 'specular'):
+            _emit_value(P, node.param(key))
+        P.emit(_lib.OP_FRESNEL)
+    else:
+        raise NotImplementedError(f'material parameter node {type(node).__name__} is not supported by the B200 rasteriser')
+
+
+def _emit_material(P, m, what):
+    """what: 'brdf' | 'ambient' | 'emission' (the three methods Lighting.shade_color calls, lighting.py:84-98)."""
+    if isinstance(m, MixMaterial):
+        _emit_value(P, m.param('factor'))
+        _emit_material(P, m.mat1, what)
+        _emit_material(P, m.mat2, what)
+        P.emit(_lib.OP_MIX)
+    elif isinstance(m, ScaleMaterial):
+        _emit_value(P, m.param('factor'))
+        _emit_material(P, m.mat, what)
+        P.emit(_lib.OP_MUL)
+    elif isinstance(m, AddMaterial):
+        _emit_material(P, m.mat1, what)
+        _emit_material(P, m.mat2, what)
+        P.emit(_lib.OP_ADD)
+    elif isinstance(m, Lambert):
+        if what == 'brdf':
+            P.emit(_lib.OP_LAMBERT)
+        else:
+            P.const(1.0 if what == 'ambient' else 0.0)
+    elif isinstance(m, Phong):
+        if what == 'brdf':
+            _emit_value(P, m.param('shineness'))
+            P.emit(_lib.OP_PHONG)
+        else:
+            P.const(1.0 if what == 'ambient' else 0.0)
+    elif isinstance(m, CookTorrance):
+        if what == 'brdf':
+            _emit_value(P, m.param('roughness'))
+            _emit_value(P, m.param('fresnel'))
+            P.emit(_lib.OP_COOK)
+        else:
+            P.const(1.0 if what == 'ambient' else 0.0)
+    elif isinstance(m, Emission):
+        P.const(1.0 if what == 'emission' else 0.0)
+    else:
+        raise NotImplementedError(f'material {type(m).__name__} is not supported by the B200 rasteriser')
+
+
+def flatten_material(material):
+    """-> (code_brdf, code_ambient, code_emission, [Texture nodes]); each code is a list of (op, arg, c3)."""
+    P = _Program()
+    out = []
+    for what in ('brdf', 'ambient', 'emission'):
+        P.code = []
+        _emit_material(P, material, what)
+        out.append(P.code)
+    total = sum(len(c) for c in out)
+    if total > _lib.TINA_MAX_INSTR:
+        raise NotImplementedError(f'material program too long ({total} > {_lib.TINA_MAX_INSTR})')
+    return out[0], out[1], out[2], P.textures
+
+
+def material_struct(material, device):
+    """Build the TinaMaterial POD; returns (struct, keepalive list of device tensors)."""
+    brdf, amb, emi, textures = flatten_material(material)
+    m = _lib.TinaMaterial()
+    m.n_brdf, m.n_ambient, m.n_emission, m.ntex = len(brdf), len(amb), len(emi), len(textures)
+    keep = []
+    for i, t in enumerate(textures):
+        d = t.device_tensor(device)
+        keep.append(d)
+        m.tex[i] = d.data_ptr()
+        m.tex_w[i], m.tex_h[i], m.tex_c[i] = d.shape[0], d.shape[1], d.shape[2]
+    for i, (op, arg, c) in enumerate(brdf + amb + emi):
+        m.code[i].op, m.code[i].arg = op, arg
+        m.code[i].c[0], m.code[i].c[1], m.code[i].c[2] = c
+    return m, keep

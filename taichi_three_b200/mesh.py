@@ -1,0 +1,302 @@
+"""Mesh providers accepted by TriangleRaster.set_object (reference tina/mesh/*.py).
+
+In the reference the mesh protocol (`pre_compute / get_nfaces / get_face_verts / norms /
+coors`) is inlined into the set_object kernel at JIT time.  Here every provider describes
+itself as a FaceSource (a base array layout + at most one transform + winding / normal mode
+bits) which TriangleRaster hands to ONE gather kernel of libtina_b200 (K0).
+"""
+import numpy as np
+import torch
+
+from .field import Field
+
+MAX = 2**20  # common.py:7
+
+
+class FaceSource:
+    def __init__(self, kind, **kw):
+        self.kind = kind  # 'simple' | 'indexed' | 'grid'
+        self.trans = None  # 4x4 float32 (mesh/trans.py)
+        self.trans_normal = None  # 3x3 float32
+        self.double_sided = False  # MeshNoCulling
+        self.flip = False  # MeshFlipCulling
+        self.negate = False  # MeshFlipNormal
+        self.__dict__.update(kw)
+
+    @property
+    def mode(self):
+        return (1 if self.double_sided else 0) | (2 if self.flip else 0) | (4 if self.negate else 0)
+
+
+def _to_device_f32(arr, device, shape_tail):
+    """numpy / torch -> contiguous float32 CUDA tensor; CUDA float32 contiguous tensors are aliased (zero-copy)."""
+    if isinstance(arr, torch.Tensor):
+        t = arr
+        if t.device.type != 'cuda' or t.dtype != torch.float32 or not t.is_contiguous():
+            t = t.to(device=device, dtype=torch.float32).contiguous()
+    else:
+        t = torch.as_tensor(np.ascontiguousarray(arr, dtype=np.float32)).to(device)
+    if tuple(t.shape[1:]) != tuple(shape_tail):
+        raise ValueError(f'expected an array of shape [N, {", ".join(map(str, shape_tail))}], got {tuple(t.shape)}')
+    return t
+
+
+def _device():
+    if not torch.cuda.is_available():
+        raise RuntimeError('taichi_three_b200 meshes live in GPU memory: a CUDA device is required (no CPU fallback)')
+    return torch.device('cuda', torch.cuda.current_device())
+
+
+class SimpleMesh:
+    """mesh/simple.py:5-115.  `set_face_*` take numpy arrays or (zero-copy) CUDA tensors."""
+
+    def __init__(self, maxfaces=MAX, npolygon=3):
+        if npolygon != 3:
+            raise NotImplementedError('only triangle meshes (npolygon=3) are on the B200 raster path')
+        self.maxfaces = maxfaces
+        self.npolygon = npolygon
+        self._verts = self._norms = self._coors = None
+        self._n = 0
+
+    def get_npolygon(self):
+        return self.npolygon
+
+    def get_nfaces(self):
+        return min(self._n, self.maxfaces)
+
+    @property
+    def nfaces(self):
+        return self.get_nfaces()
+
+    def _check(self, t):
+        if t.shape[0] > self.maxfaces:
+            # the reference truncates silently (simple.py:63); overflowing is almost always a bug
+            raise ValueError(f'{t.shape[0]} faces exceed maxfaces={self.maxfaces}: pass SimpleMesh(maxfaces=...)')
+        return t
+
+    def set_face_verts(self, verts):  # simple.py:53-67
+        self._verts = self._check(_to_device_f32(verts, _device(), (3, 3)))
+        self._n = self._verts.shape[0]
+
+    def set_face_norms(self, norms):  # simple.py:69-83
+        self._norms = self._check(_to_device_f32(norms, _device(), (3, 3)))
+
+    def set_face_coors(self, coors):  # simple.py:85-98
+        if not isinstance(coors, torch.Tensor):
+            coors = np.asarray(coors)[:, :, :2]
+        self._coors = self._check(_to_device_f32(coors, _device(), (3, 2)))
+
+    @property
+    def verts(self):
+        return Field(self._verts)
+
+    @property
+    def norms(self):
+        return Field(self._norms)
+
+    @property
+    def coors(self):
+        return Field(self._coors)
+
+    def _source(self):
+        return FaceSource('simple', verts=self._verts, norms=self._norms, coors=self._coors, nfaces=self.get_nfaces())
+
+
+class MeshModel:
+    """mesh/model.py:5-73: indexed mesh from an OBJ dict {'v','vt','vn','f'} or a path."""
+
+    def __init__(self, obj, *args, **kwargs):
+        if isinstance(obj, str):
+            from .assimp import readobj
+            obj = readobj(obj, *args, **kwargs)
+        dev = _device()
+        faces = np.asarray(obj['f'])
+        if faces.ndim == 2:  # model.py:23-24: same index for v / vt / vn
+            faces = np.stack([faces, faces, faces], axis=2)
+        self.faces = torch.as_tensor(np.ascontiguousarray(faces.astype(np.uint32).astype(np.int64).astype(np.int32))).to(dev)
+        v = np.asarray(obj['v'], dtype=np.float32)
+        vt = np.asarray(obj.get('vt', np.zeros((1, 2))), dtype=np.float32)[:, :2]
+        vn = np.asarray(obj.get('vn', np.zeros((1, 3))), dtype=np.float32)
+        self.verts = torch.as_tensor(np.ascontiguousarray(v)).to(dev)
+        self.coors = torch.as_tensor(np.ascontiguousarray(vt)).to(dev)
+        self.norms = torch.as_tensor(np.ascontiguousarray(vn)).to(dev)
+        self.maxfaces, self.maxverts = len(faces), len(v)
+        self.maxcoors, self.maxnorms = len(vt), len(vn)
+        self._host = {'f': faces.astype(np.int64), 'v': v}
+
+    def get_npolygon(self):
+        return 3
+
+    def get_max_vert_nindex(self):
+        return self.maxverts
+
+    def get_nfaces(self):
+        return self.maxfaces
+
+    def _source(self):
+        return FaceSource('indexed', v=self.verts, vt=self.coors, vn=self.norms, faces=self.faces, nfaces=self.maxfaces)
+
+
+class MeshGrid:
+    """mesh/grid.py:5-70: (nx, ny) vertex grid, two triangles per cell; normals are recomputed
+    from `pos` every frame by the set_object kernel (grid.py:26-35)."""
+
+    def __init__(self, res, as_quad=False):
+        if as_quad:
+            raise NotImplementedError('as_quad grids feed the wireframe raster, which is not on this path')
+        if isinstance(res, int):
+            res = res, res
+        self.res = (int(res[0]), int(res[1]))
+        nx, ny = self.res
+        dev = _device()
+        # grid.py:17-21 (f32 arithmetic: I / (res - 1), u * 2 - 1)
+        u = (np.arange(nx, dtype=np.float32) / np.float32(nx - 1))[:, None] * np.ones((1, ny), np.float32)
+        v = np.ones((nx, 1), np.float32) * (np.arange(ny, dtype=np.float32) / np.float32(ny - 1))[None, :]
+        pos = np.stack([u * np.float32(2) - np.float32(1), v * np.float32(2) - np.float32(1), np.zeros_like(u)], axis=2)
+        self._pos = torch.as_tensor(np.ascontiguousarray(pos, dtype=np.float32)).to(dev)
+        self._tex = torch.as_tensor(np.ascontiguousarray(np.stack([u, v], axis=2), dtype=np.float32)).to(dev)
+        self.as_quad = False
+
+    @property
+    def pos(self):
+        """float32[nx, ny, 3] device field; edit through `.to_torch()` (in place) or `.from_numpy()`."""
+        return Field(self._pos)
+
+    @property
+    def tex(self):
+        return Field(self._tex)
+
+    def get_npolygon(self):
+        return 3
+
+    def get_nfaces(self):
+        return 2 * (self.res[0] - 1) * (self.res[1] - 1)
+
+    def _source(self):
+        return FaceSource('grid', pos=self._pos, nx=self.res[0], ny=self.res[1], nfaces=self.get_nfaces())
+
+
+class MeshEditBase:
+    def __init__(self, mesh):
+        self.mesh = mesh
+
+    def __getattr__(self, attr):
+        return getattr(self.__dict__['mesh'], attr)
+
+    def _source(self):
+        return self.mesh._source()
+
+
+class MeshTransform(MeshEditBase):
+    """mesh/trans.py:5-40."""
+
+    def __init__(self, mesh, trans=None):
+        super().__init__(mesh)
+        self.trans = np.eye(4, dtype=np.float32)
+        self.trans_normal = np.eye(3, dtype=np.float32)
+        if trans is not None:
+            self.set_transform(trans)
+
+    def set_transform(self, trans):
+        trans = np.asarray(trans, dtype=np.float64)
+        self.trans = trans.astype(np.float32)
+        # trans.py:23-26: inverse transpose, upper-left 3x3 kept by the 3x3 field
+        self.trans_normal = np.transpose(np.linalg.inv(trans))[:3, :3].astype(np.float32)
+
+    def _source(self):
+        s = self.mesh._source()
+        if s.trans is not None:
+            raise NotImplementedError('nested MeshTransform is not supported: pre-multiply the matrices')
+        s.trans, s.trans_normal = self.trans, self.trans_normal
+        return s
+
+
+class MeshFlipCulling(MeshEditBase):
+    """mesh/cull.py:5-28: reversed winding."""
+
+    def _source(self):
+        s = self.mesh._source()
+        if s.double_sided:
+            raise NotImplementedError('MeshFlipCulling(MeshNoCulling(...)) is not supported')
+        s.flip = not s.flip
+        return s
+
+
+class MeshNoCulling(MeshEditBase):
+    """mesh/cull.py:31-57: every face twice, odd copies reversed with negated normals."""
+
+    def get_nfaces(self):
+        return self.mesh.get_nfaces() * 2
+
+    def _source(self):
+        s = self.mesh._source()
+        if s.double_sided:
+            raise NotImplementedError('nested MeshNoCulling is not supported')
+        s.double_sided = True
+        return s
+
+
+class MeshFlipNormal(MeshEditBase):
+    """mesh/cull.py:60-66."""
+
+    def _source(self):
+        s = self.mesh._source()
+        s.negate = not s.negate
+        return s
+
+
+def _face_normals(v, f):
+    a, b, c = v[f[:, 0]], v[f[:, 1]], v[f[:, 2]]
+    n = np.cross(b - a, c - a).astype(np.float32)
+    ln = np.sqrt((n * n).sum(axis=1, keepdims=True)).astype(np.float32)
+    return (np.float32(1) / ln) * n
+
+
+class MeshFlatNormal(MeshEditBase):
+    """mesh/norm.py:5-14: per-face normal for all three corners (MeshModel sources)."""
+
+    def _source(self):
+        s = self.mesh._source()
+        if s.kind != 'indexed':
+            raise NotImplementedError('MeshFlatNormal needs an indexed mesh')
+        host = self.mesh._host
+        fv = host['f'][:, :, 0]
+        nrm = _face_normals(host['v'], fv)
+        faces = host['f'].copy()
+        faces[:, :, 2] = np.arange(len(faces))[:, None]
+        s.vn = torch.as_tensor(np.ascontiguousarray(nrm)).to(s.v.device)
+        s.faces = torch.as_tensor(np.ascontiguousarray(faces.astype(np.int32))).to(s.v.device)
+        return s
+
+
+class MeshSmoothNormal(MeshEditBase):
+    """mesh/norm.py:17-55: area-unweighted average of adjacent face normals per vertex.
+    (The reference accumulates with atomics in arbitrary order; this sums in face order.)"""
+
+    def __init__(self, mesh, cached=True):
+        super().__init__(mesh)
+        self.cached = cached
+        self._norm = None
+
+    def update_normal(self):
+        host = self.mesh._host
+        fv = host['f'][:, :, 0]
+        fn = _face_normals(host['v'], fv)
+        acc = np.zeros((len(host['v']), 3), dtype=np.float32)
+        for k in range(3):
+            np.add.at(acc, fv[:, k], fn)
+        ln = np.sqrt((acc * acc).sum(axis=1, keepdims=True)).astype(np.float32)
+        with np.errstate(divide='ignore', invalid='ignore'):
+            self._norm = ((np.float32(1) / ln) * acc).astype(np.float32)
+
+    def _source(self):
+        s = self.mesh._source()
+        if s.kind != 'indexed':
+            raise NotImplementedError('MeshSmoothNormal needs an indexed mesh')
+        if self._norm is None or not self.cached:
+            self.update_normal()
+        faces = self.mesh._host['f'].copy()
+        faces[:, :, 2] = faces[:, :, 0]
+        s.vn = torch.as_tensor(np.ascontiguousarray(self._norm)).to(s.v.device)
+        s.faces = torch.as_tensor(np.ascontiguousarray(faces.astype(np.int32))).to(s.v.device)
+        return s

@@ -1,0 +1,122 @@
+"""Scene: frame orchestration for the raster pipeline (reference tina/scene/raster.py:5-258),
+restricted to the triangle-raster path: objects -> set_object / render_occup / render_color,
+default light + ambient, ACES tonemap.  Options that enable other subsystems (ibl, ssr, ssao,
+fxaa, blooming, taa) are outside this path and raise."""
+import numpy as np
+import torch
+
+from . import _lib
+from .engine import Engine, _stream
+from .field import Field
+from .lighting import Lighting
+from .material import Diffuse
+from .shader import Shader, ShaderGroup
+from .triangle import TriangleRaster
+
+import ctypes as C
+
+
+class _ObjInfo:
+    def __init__(self, material, raster):
+        self.material, self.raster = material, raster
+
+
+class Scene:
+    UNSUPPORTED = ('taa', 'ibl', 'ssr', 'ssao', 'fxaa', 'blooming')
+
+    def __init__(self, res_x=512, res_y=None, **options):
+        self.engine = Engine(res_x, res_y)
+        self.res = self.engine.res
+        self.options = options
+        for key in self.UNSUPPORTED:
+            if options.get(key, False):
+                raise NotImplementedError(f'Scene option {key}=True is outside the B200 triangle-raster path')
+        self.tonemap = options.get('tonemap', True)
+        self.bgcolor = options.get('bgcolor', 0)
+        self.lighting = Lighting()
+        self.image = Field(torch.zeros((self.res[0], self.res[1], 3), dtype=torch.float32, device=self.engine.device))
+        self.default_material = Diffuse()
+        self.post_shaders = []
+        self.pre_shaders = []
+        self.materials = []
+        self.shaders = {}
+        self.objects = {}
+        self.pp_img = self.image
+        # raster.py:90-93
+        self.lighting.add_light(dir=[1, 2, 3], color=[0.9, 0.9, 0.9])
+        self.lighting.set_ambient_light([0.1, 0.1, 0.1])
+
+    def _ensure_material_shader(self, material):  # raster.py:95-110
+        if any(material is m for m in self.materials):
+            return
+        shader = Shader(self.image, self.lighting, material)
+        self.materials.append(material)
+        self.shaders[id(material)] = ShaderGroup(self.pre_shaders + [shader] + self.post_shaders)
+
+    def add_object(self, object, material=None, raster=None):  # raster.py:112-146
+        assert id(object) not in self.objects
+        if material is None:
+            material = self.default_material
+        if raster is None:
+            if hasattr(object, 'get_nfaces') and not (hasattr(object, 'get_npolygon') and object.get_npolygon() == 2):
+                if not hasattr(self, 'triangle_raster'):
+                    opts = {k: v for k, v in self.options.items() if k in ('maxfaces', 'smoothing', 'texturing', 'culling', 'clipping')}
+                    self.triangle_raster = TriangleRaster(self.engine, **opts)
+                raster = self.triangle_raster
+            elif hasattr(object, 'get_nfaces') or hasattr(object, 'get_npars') or hasattr(object, 'sample_volume'):
+                raise NotImplementedError('wireframe / particle / volume rasterisers are outside the B200 triangle path')
+            else:
+                raise ValueError(f'cannot determine raster type of object: {object}')
+        self._ensure_material_shader(material)
+        self.objects[id(object)] = (object, _ObjInfo(material, raster))
+
+    def init_control(self, gui, center=None, theta=None, phi=None, radius=None, fov=60, is_ortho=False, blendish=True):
+        from .control import Control
+        self.control = Control(gui, fov=fov, is_ortho=is_ortho, blendish=blendish)
+        if center is not None:
+            self.control.center[:] = center
+        self.control.init_rot(theta, phi)
+        if radius is not None:
+            self.control.radius = radius
+
+    def render(self):
+        """raster.py:168-207.  image.fill(bg) is fused into the first object's shading pass and, for
+        single-object scenes, so is the ACES tonemap; results are identical to the separate passes."""
+        self.engine.clear_depth()
+        for s in self.pre_shaders + self.post_shaders:
+            s.clear_buffer()
+        items = list(self.objects.values())
+        bg = np.broadcast_to(np.asarray(self.bgcolor, dtype=np.float32), (3,))
+        if not items:
+            self.image.fill(bg)
+        fuse_tm = bool(self.tonemap) and len(items) == 1
+        for i, (obj, info) in enumerate(items):
+            shader = self.shaders[id(info.material)]
+            info.raster.set_object(obj)
+            info.raster.render_occup()
+            if isinstance(info.raster, TriangleRaster):
+                info.raster.render_color(shader, fill_bg=bg if i == 0 else None, tonemap=fuse_tm)
+            else:
+                if i == 0:
+                    self.image.fill(bg)
+                info.raster.render_color(shader)
+        if self.tonemap and not fuse_tm:
+            t = self.image.to_torch()
+            _lib.check(_lib.lib().tina_image_tonemap(C.c_void_p(t.data_ptr()), t.numel(), _stream()))
+
+    @property
+    def img(self):
+        return self.pp_img
+
+    def input(self, gui):  # raster.py:216-228
+        if not hasattr(self, 'control'):
+            from .control import Control
+            self.control = Control(gui)
+        return self.control.apply_camera(self.engine)
+
+    def clear(self):
+        pass
+
+    def load_gltf(self, path):  # raster.py:234-241
+        from .assimp import readgltf
+        return readgltf(path).extract(self)

@@ -1,0 +1,195 @@
+"""TriangleRaster: drop-in for the reference's tina/core/triangle.py:4-153 on top of
+libtina_b200 (hand-written sm_100a kernels, C ABI in include/tina_b200.h)."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .engine import _stream
+from .field import Field, wrap_device
+from .material import material_struct
+from .mesh import MAX, FaceSource, _to_device_f32
+from .shader import Shader, ShaderGroup
+
+
+def _fp(a):
+    if a is None:
+        return None
+    return np.ascontiguousarray(a, dtype=np.float32).ctypes.data_as(C.POINTER(C.c_float))
+
+
+class TriangleRaster:
+    def __init__(self, engine, maxfaces=MAX, smoothing=False, texturing=False, culling=True, clipping=True,
+                 **extra_options):
+        self.engine = engine
+        self.res = engine.res
+        self.maxfaces = maxfaces
+        self.smoothing, self.texturing = bool(smoothing), bool(texturing)
+        self.culling, self.clipping = bool(culling), bool(clipping)
+        self.flags = ((_lib.TINA_SMOOTHING if smoothing else 0) | (_lib.TINA_TEXTURING if texturing else 0) |
+                      (_lib.TINA_CULLING if culling else 0) | (_lib.TINA_CLIPPING if clipping else 0))
+        L = _lib.lib()
+        h = C.c_void_p()
+        _lib.check(L.tina_raster_create(C.byref(h), engine._h, int(maxfaces), self.flags))
+        self._h = h
+        self._keep = []  # tensors the C side currently aliases
+        self._occup = None
+        self._occup_stale = True
+        self._direct = {}  # set_face_* fast path staging
+
+    def __del__(self):
+        try:
+            if getattr(self, '_h', None):
+                _lib.lib().tina_raster_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    # ---- set_object (triangle.py:72-86) ------------------------------------------------
+    def set_object(self, mesh):
+        if not hasattr(mesh, '_source'):
+            raise TypeError(f'{type(mesh).__name__} does not describe itself as a FaceSource; '
+                            'use tina SimpleMesh / MeshModel / MeshGrid / MeshTransform / MeshNoCulling ...')
+        self._set_source(mesh._source())
+
+    def _set_source(self, s: FaceSource):
+        L = _lib.lib()
+        st = _stream()
+        n = int(s.nfaces)
+        # (the reference never checks maxfaces here and overruns its fields, triangle.py:74-78)
+        total = n * (2 if s.double_sided else 1)
+        if total > self.maxfaces:
+            raise ValueError(f'{total} faces exceed maxfaces={self.maxfaces}: pass maxfaces=... to Scene / TriangleRaster')
+        trans = _fp(s.trans) if s.trans is not None else None
+        tn = _fp(s.trans_normal) if s.trans is not None else None
+        keep = []
+        if s.kind == 'simple' and s.trans is None and s.mode == 0:
+            v, nn, tt = s.verts, s.norms if self.smoothing else None, s.coors if self.texturing else None
+            if n and v is None:
+                raise ValueError('SimpleMesh has no vertices: call set_face_verts first')
+            if n and self.smoothing and nn is None:
+                raise ValueError('smoothing=True needs set_face_norms')
+            if n and self.texturing and tt is None:
+                raise ValueError('texturing=True needs set_face_coors')
+            keep = [v, nn, tt]
+            ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None and n else None
+            _lib.check(L.tina_raster_set_faces(self._h, ptr(v), ptr(nn), ptr(tt), n, 1, st))
+        elif s.kind in ('simple', 'indexed'):
+            if s.kind == 'simple':  # wrapped SimpleMesh: trivial index buffer -> general gather
+                idx = torch.arange(n * 3, dtype=torch.int32, device=s.verts.device).view(n, 3, 1).expand(n, 3, 3).contiguous()
+                v, vt, vn, faces = s.verts.view(-1, 3), s.coors, s.norms, idx
+                vt = vt.view(-1, 2) if vt is not None else None
+                vn = vn.view(-1, 3) if vn is not None else None
+            else:
+                v, vt, vn, faces = s.v, s.vt, s.vn, s.faces
+            if self.smoothing and vn is None:
+                raise ValueError('smoothing=True needs normals')
+            if self.texturing and vt is None:
+                raise ValueError('texturing=True needs texture coordinates')
+            keep = [v, vt, vn, faces]
+            ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+            _lib.check(L.tina_raster_set_faces_indexed(self._h, ptr(v), ptr(vt) if self.texturing else None,
+                                                       ptr(vn) if self.smoothing else None, ptr(faces), n, trans, tn,
+                                                       s.mode, st))
+        elif s.kind == 'grid':
+            keep = [s.pos]
+            _lib.check(L.tina_raster_set_faces_grid(self._h, C.c_void_p(s.pos.data_ptr()), s.nx, s.ny, trans, tn, s.mode, st))
+        else:
+            raise ValueError(s.kind)
+        self._keep = keep
+        self._occup_stale = True
+
+    # north-star fast path: feed face arrays straight to the raster (zero-copy for CUDA tensors)
+    def set_face_verts(self, verts):
+        self._direct = {'verts': _to_device_f32(verts, self.engine.device, (3, 3))}
+        self._apply_direct()
+
+    def set_face_norms(self, norms):
+        self._direct['norms'] = _to_device_f32(norms, self.engine.device, (3, 3))
+        self._apply_direct()
+
+    def set_face_coors(self, coors):
+        self._direct['coors'] = _to_device_f32(coors, self.engine.device, (3, 2))
+        self._apply_direct()
+
+    def _apply_direct(self):
+        d = self._direct
+        if 'verts' not in d or (self.smoothing and 'norms' not in d) or (self.texturing and 'coors' not in d):
+            return
+        self._set_source(FaceSource('simple', verts=d['verts'], norms=d.get('norms'), coors=d.get('coors'),
+                                    nfaces=d['verts'].shape[0]))
+
+    # ---- render_occup (triangle.py:89-131) ---------------------------------------------
+    def render_occup(self):
+        _lib.check(_lib.lib().tina_raster_render_occup(self._h, _stream()))
+        self._occup_stale = True
+
+    # ---- render_color (triangle.py:134-153) --------------------------------------------
+    def render_color(self, shader, fill_bg=None, tonemap=False):
+        """`shader`: a Shader or a ShaderGroup of Shaders.  fill_bg / tonemap are fusion hints used by Scene.render."""
+        shaders = shader.shaders if isinstance(shader, ShaderGroup) else [shader]
+        for s in shaders:
+            if not isinstance(s, Shader):
+                raise NotImplementedError(f'{type(s).__name__} is not supported by the B200 render_color yet')
+            img = s.img.to_torch() if hasattr(s.img, 'to_torch') else s.img
+            if img.dtype != torch.float32 or not img.is_contiguous() or img.numel() != self.res[0] * self.res[1] * 3:
+                raise ValueError('shader image must be a contiguous float32 [W, H, 3] CUDA tensor')
+            mat, keep = material_struct(s.material, self.engine.device)
+            light = s.lighting.struct()
+            flags = (_lib.TINA_COLOR_TONEMAP if tonemap else 0) | (_lib.TINA_COLOR_FILL_BG if fill_bg is not None else 0)
+            bg = _fp(np.broadcast_to(np.asarray(fill_bg if fill_bg is not None else 0, dtype=np.float32), (3,)))
+            _lib.check(_lib.lib().tina_raster_render_color(self._h, C.byref(mat), C.byref(light), C.c_void_p(img.data_ptr()),
+                                                           flags, bg, _stream()))
+            self._mat_keep = keep
+
+    # ---- public state ------------------------------------------------------------------
+    @property
+    def occup(self):
+        """int32[W, H] face id per pixel, -1 = none (triangle.py:16), for the last render_occup."""
+        if self._occup is None:
+            self._occup = torch.empty(self.res, dtype=torch.int32, device=self.engine.device)
+        if self._occup_stale:
+            _lib.check(_lib.lib().tina_raster_occup(self._h, C.c_void_p(self._occup.data_ptr()), _stream()))
+            self._occup_stale = False
+        return Field(self._occup)
+
+    def _buffers(self):
+        v, n, t, nf = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_int64()
+        _lib.check(_lib.lib().tina_raster_buffers(self._h, C.byref(v), C.byref(n), C.byref(t), C.byref(nf)))
+        return v.value, n.value, t.value, nf.value
+
+    @property
+    def nfaces(self):
+        return self._buffers()[3]
+
+    @property
+    def verts(self):
+        v, _, _, nf = self._buffers()
+        return Field(wrap_device(v, (nf, 3, 3), torch.float32, self.engine.device, owner=self))
+
+    @property
+    def norms(self):
+        _, n, _, nf = self._buffers()
+        return Field(wrap_device(n, (nf, 3, 3), torch.float32, self.engine.device, owner=self))
+
+    @property
+    def coors(self):
+        _, _, t, nf = self._buffers()
+        return Field(wrap_device(t, (nf, 3, 2), torch.float32, self.engine.device, owner=self))
+
+    def set_tuning(self, tiny_max=None, force_tiles=None, collect_stats=None):
+        """Strategy knobs (every setting produces identical bits): max bbox area rasterised per
+        thread in the setup kernel; force every face through the binned tile path."""
+        L = _lib.lib()
+        if tiny_max is not None:
+            _lib.check(L.tina_raster_set_tuning(self._h, 0, int(tiny_max)))
+        if force_tiles is not None:
+            _lib.check(L.tina_raster_set_tuning(self._h, 2, int(force_tiles)))
+        if collect_stats is not None:
+            _lib.check(L.tina_raster_set_tuning(self._h, 3, int(collect_stats)))
+
+    def stats(self):
+        out = (C.c_int64 * 6)()
+        _lib.check(_lib.lib().tina_raster_stats(self._h, out))
+        return dict(zip(('culled', 'clipped', 'direct', 'warp', 'queued', 'tile_entries'), list(out)))

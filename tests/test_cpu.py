@@ -1,0 +1,149 @@
+"""CPU-only tests (`-m "not gpu"`): the oracle against known answers, the host-side logic of the
+Python mirror, and that the C-ABI library loads and exports every symbol include/tina_b200.h declares."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import scenes
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ---- oracle known answers (SURVEY.md §8c probes, measured with an independent NumPy restatement) ----
+def test_oracle_monkey_probe(O, tina):
+    v, _, _ = O.indexed(scenes.load_monkey())
+    assert v.shape == (968, 3, 3)
+    view, proj = scenes.default_camera()
+    W2V = (proj @ view).astype(np.float32)
+    assert np.allclose(W2V, [[1.7320508, 0, 0, 0], [0, 1.7320508, 0, 0], [0, 0, -1.0002, 2.90059], [0, 0, -1, 3]], atol=1e-6)
+    occup, depth, tie, st = O.render_occup(v, W2V, 512, 512)
+    assert st['rasterised'] == 614 and st['culled'] == 354
+    assert (occup >= 0).sum() == 64082 and tie.sum() == 0
+    d = depth[occup >= 0]
+    assert 1.0239e9 < d.min() < 1.0241e9 and 1.0431e9 < d.max() < 1.0433e9
+    assert ((depth == 2**30) == (occup == -1)).all()
+
+
+def test_oracle_meshgrid_probe(O):
+    pos, _ = O.grid_positions(64, 64)
+    view, proj = scenes.default_camera()
+    W2V = (proj @ view).astype(np.float32)
+    occup, depth, tie, st = O.render_occup(O.grid_faces(pos), W2V, 512, 512)
+    assert (occup >= 0).sum() == 87616 and tie.sum() == 160
+
+
+def test_oracle_serial_semantics(O):
+    """lowest face id wins exact ties; a later pass only wins with strictly smaller depth."""
+    tri = np.array([[[-1, -1, 0], [1, -1, 0], [0, 1, 0]]], np.float32)
+    two = np.concatenate([tri, tri])
+    view, proj = scenes.default_camera()
+    W2V = (proj @ view).astype(np.float32)
+    occup, depth, tie, _ = O.render_occup(two, W2V, 64, 64)
+    assert set(np.unique(occup)) == {-1, 0} and tie[occup == 0].all()
+    occup2, depth2, _, _ = O.render_occup(tri, W2V, 64, 64, depth=depth)
+    assert (occup2 == -1).all() and np.array_equal(depth2, depth)
+
+
+def test_oracle_parallel_matches_serial_away_from_ties(O):
+    tri = scenes.soup(20000, 160, 120, s=0.03, seed=4)
+    view, proj = scenes.default_camera(160 / 120)
+    W2V = (proj @ view).astype(np.float32)
+    o1, d1, tie, _ = O.render_occup(tri, W2V, 160, 120)
+    o2, d2, _, _ = O.render_occup(tri, W2V, 160, 120, parallel=True)
+    assert np.array_equal(d1, d2)
+    assert np.array_equal(o1[tie == 0], o2[tie == 0])
+
+
+# ---- host logic ---------------------------------------------------------------------------------------
+def test_material_flattening(tina):
+    from taichi_three_b200 import _lib as L
+    brdf, amb, emi, tex = tina.flatten_material(tina.Diffuse())
+    assert [i[0] for i in brdf] == [L.OP_INPUT, L.OP_LAMBERT, L.OP_MUL] and brdf[0][1] == 1
+    brdf, amb, emi, tex = tina.flatten_material(tina.Classic())
+    assert [i[0] for i in brdf] == [L.OP_CONST, L.OP_INPUT, L.OP_LAMBERT, L.OP_MUL, L.OP_CONST, L.OP_PHONG, L.OP_MIX]
+    assert brdf[0][2] == (0.4, 0.4, 0.4) and brdf[4][2] == (32.0, 32.0, 32.0)
+    img = np.zeros((4, 4, 3), np.uint8)
+    brdf, amb, emi, tex = tina.flatten_material(tina.PBR(basecolor=tina.Texture(img), metallic=0.0, roughness=0.5))
+    assert len(tex) == 1 and [i[0] for i in brdf].count(L.OP_TEXTURE) == 3 and brdf[-1][0] == L.OP_MIX
+    with pytest.raises(TypeError):
+        tina.Phong(shininess=3)
+    with pytest.raises(ValueError):
+        tina.Input('nonsense')
+    m = tina.Lambert() * [1, 0, 0] + tina.Emission() * 0.5
+    brdf, amb, emi, _ = tina.flatten_material(m)
+    assert emi[-1][0] == L.OP_ADD
+
+
+def test_loaders(tina):
+    obj = scenes.load_monkey()
+    assert obj['f'].shape == (968, 3, 3) and obj['v'].shape == (507, 3)
+    g = scenes.load_cornell()
+    prims = [p for n in g.nodes for p in n.primitives]
+    assert [len(p.obj['f']) for p in prims] == [12, 12, 10]
+    assert g.images[0].shape == (512, 512, 3)
+    mat = g._material(prims[2].material)
+    assert isinstance(mat, tina.MixMaterial)
+    # node TRS: +90 degrees about X
+    assert np.allclose(g.nodes[1].trans[:3, :3] @ [0, 0, 1], [0, -1, 0], atol=1e-6)
+
+
+def test_camera_matrices(tina):
+    p = tina.perspective(60, 16 / 9)
+    assert np.isclose(p[1, 1], 1 / np.tan(np.radians(30))) and np.isclose(p[0, 0], p[1, 1] * 9 / 16) and p[3, 2] == -1
+    v = tina.lookat()
+    assert np.allclose(v @ [0, 0, 3, 1], [0, 0, 0, 1])
+    view, proj = tina.orbit_camera(center=(0, 2, 0), radius=6, theta=0.2, phi=0.5)
+    eye = np.linalg.inv(view)[:3, 3]
+    assert np.isclose(np.linalg.norm(eye - [0, 2, 0]), 6)
+
+    class G:
+        res = (640, 360)
+    c = tina.Control(G())
+    assert np.allclose(c.get_camera()[1], tina.perspective(60, 640 / 360))
+    R = tina.RotationStep(np.eye(4), 0.1, 0.0, 0.0)
+    assert np.allclose(R[:3, :3] @ R[:3, :3].T, np.eye(3), atol=1e-12)
+
+
+def test_lighting_struct(tina):
+    L = tina.Lighting()
+    L.add_light(dir=[1, 2, 3], color=[0.9, 0.9, 0.9])
+    L.add_light(pos=[1, 1, 1])
+    s = L.struct()
+    assert s.nlights == 2 and s.dirs[0][3] == 0 and s.dirs[1][3] == 1
+    assert np.isclose(np.linalg.norm(list(s.dirs[0])[:3]), 1, atol=1e-6)
+
+
+# ---- the C ABI ----------------------------------------------------------------------------------------
+def test_cabi_exports_every_declared_symbol():
+    from taichi_three_b200 import _lib
+    header = open(os.path.join(ROOT, 'include', 'tina_b200.h')).read()
+    declared = set(re.findall(r'\b(tina_[a-z0-9_]+)\s*\(', header))
+    assert len(declared) >= 20
+    so = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(so, name), f'{name} declared in include/tina_b200.h but not exported'
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert _lib.lib().tina_version() == 100
+    # struct layouts agree with the header
+    assert ctypes.sizeof(_lib.TinaInstr) == 20 and ctypes.sizeof(_lib.TinaLighting) == 16 * 16 * 2 + 16 + 16
+
+
+def test_no_cpu_fallback(tina):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    with pytest.raises(RuntimeError):
+        tina.Engine(64)
+    with pytest.raises(RuntimeError):
+        tina.MeshGrid(8)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, 'taichi_three_b200')
+    for fn in os.listdir(pkg):
+        if fn.endswith('.py'):
+            assert 'oracle' not in open(os.path.join(pkg, fn)).read(), fn
+    assert 'oracle' not in open(os.path.join(pkg, 'csrc', 'tina_b200.cu')).read().replace('the serial CPU restatement', '')

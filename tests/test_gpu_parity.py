@@ -1,0 +1,265 @@
+"""GPU parity tests: the CUDA path (through the Python mirror -> C ABI -> sm_100a kernels)
+against the CPU oracle on the same seeded inputs.
+
+Bars: face-id (`occup`) and integer `depth` buffers BIT-EXACT vs the serial
+oracle, exact-depth ties included; colour within 1e-4 abs in fp32, before and after tonemap.
+"""
+import numpy as np
+import pytest
+
+import scenes
+
+pytestmark = pytest.mark.gpu
+
+COLOR_TOL = 1e-4  # north_star: "colour buffers match within 1e-4 abs in fp32"
+
+
+def _flags(O, smoothing=False, texturing=False, culling=True, clipping=True):
+    return ((O.SMOOTHING if smoothing else 0) | (O.TEXTURING if texturing else 0) | (O.CULLING if culling else 0) |
+            (O.CLIPPING if clipping else 0))
+
+
+def _check_frame(scene, ref, tol=COLOR_TOL):
+    import torch
+    torch.cuda.synchronize()
+    depth = scene.engine.depth.to_numpy()
+    occup = scene.triangle_raster.occup.to_numpy()
+    assert np.array_equal(depth, ref['depth']), f"depth differs at {(depth != ref['depth']).sum()} px"
+    assert np.array_equal(occup, ref['occups'][-1]), f"occup differs at {(occup != ref['occups'][-1]).sum()} px"
+    img = scene.img.to_numpy()
+    err = np.abs(img - ref['image']).max()
+    assert err <= tol, f'colour max abs err {err}'
+    return err
+
+
+def test_monkey_flat_diffuse(tina, O):
+    """C1: docs/monkey.py -- Suzanne, 512x512, flat shading, default light/material/camera."""
+    obj = scenes.load_monkey()
+    scene = tina.Scene()
+    scene.add_object(tina.MeshModel(obj))
+    view, proj = scenes.default_camera()
+    scene.engine.set_camera(view, proj)
+    scene.render()
+    v, _, _ = O.indexed(obj)
+    ref = O.render_scene([(v, None, None, tina.Diffuse())], 512, 512, view, proj, scene.lighting, _flags(O))
+    _check_frame(scene, ref)
+    assert (ref['depth'] < 2**30).sum() == 64082  # SURVEY §8c probe
+    # pre-tonemap image too: render without the fused tonemap
+    scene2 = tina.Scene(tonemap=False)
+    scene2.add_object(tina.MeshModel(obj))
+    scene2.engine.set_camera(view, proj)
+    scene2.render()
+    assert np.abs(scene2.img.to_numpy() - ref['pre_tonemap']).max() <= COLOR_TOL
+
+
+@pytest.mark.parametrize('nocull', [False, True])
+def test_meshgrid_wave_smooth_classic(tina, O, nocull):
+    """C2-style at test size: MeshGrid wave, smooth normals, Classic (Lambert + Phong); ties present."""
+    n, W, H = 96, 640, 360
+    pos = scenes.wave_grid_pos(n)
+    scene = tina.Scene((W, H), smoothing=True)
+    grid = tina.MeshGrid(n)
+    grid.pos.from_numpy(pos)
+    scene.add_object(tina.MeshNoCulling(grid) if nocull else grid, tina.Classic())
+    view, proj = scenes.default_camera(W / H)
+    scene.engine.set_camera(view, proj)
+    scene.render()
+    fv, fn = O.grid_faces(pos), O.grid_faces(O.grid_normals(pos))
+    if nocull:
+        fv, fn, _ = O.no_culling(fv, fn)
+    ref = O.render_scene([(fv, fn, None, tina.Classic())], W, H, view, proj, scene.lighting, _flags(O, smoothing=True))
+    _check_frame(scene, ref)
+    # set_object itself: raster.verts / raster.norms equal the oracle's expansion bit for bit
+    assert np.array_equal(scene.triangle_raster.verts.to_numpy(), fv)
+    assert np.array_equal(scene.triangle_raster.norms.to_numpy(), fn)
+
+
+def test_cornell_gltf_pbr_textured(tina, O):
+    """C4 at test size: cornell.gltf, 3 objects, smoothing + texturing, PBR (CookTorrance + texture)."""
+    W = H = 256
+    for k, (view, proj) in enumerate(scenes.cornell_views(4)):
+        gltf = scenes.load_cornell()
+        scene = tina.Scene((W, H), smoothing=True, texturing=True)
+        gltf.extract(scene)
+        assert len(scene.objects) == 3
+        scene.engine.set_camera(view, proj)
+        scene.render()
+        ref = O.render_scene(scenes.cornell_oracle_objects(gltf), W, H, view, proj, scene.lighting,
+                             _flags(O, smoothing=True, texturing=True))
+        _check_frame(scene, ref)
+        assert (ref['depth'] < 2**30).mean() > 0.5
+
+
+def _render_soup(tina, tri, W, H, view, proj, **tuning):
+    scene = tina.Scene((W, H), maxfaces=len(tri))
+    mesh = tina.SimpleMesh(maxfaces=len(tri))
+    mesh.set_face_verts(tri)
+    scene.add_object(mesh)
+    scene.engine.set_camera(view, proj)
+    scene.triangle_raster.set_tuning(**tuning)
+    scene.render()
+    return scene
+
+
+@pytest.mark.parametrize('tuning', [dict(), dict(tiny_max=0), dict(tiny_max=4), dict(tiny_max=100000), dict(force_tiles=1)])
+def test_soup_depth_complexity_all_strategies(tina, O, tuning):
+    """C3-style at test size: random soup with depth complexity ~8; every rasteriser strategy
+    (per-thread direct / binned tile path / mixtures) must give the same bits."""
+    W, H, n = 320, 200, 60000
+    view, proj = scenes.default_camera(W / H)
+    tri = scenes.soup(n, W, H, s=0.012, seed=11)
+    scene = _render_soup(tina, tri, W, H, view, proj, **tuning)
+    ref = O.render_scene([(tri, None, None, tina.Diffuse())], W, H, view, proj, scene.lighting, _flags(O))
+    _check_frame(scene, ref)
+    assert ref['ties'][0].sum() >= 0
+
+
+def test_mixed_sizes_and_edge_cases(tina, O):
+    """Triangles behind the camera (w <= 0), NaN / inf vertices, zero-area, off-screen, screen-filling
+    with every vertex outside the NDC cube (dropped by the per-vertex clip test, triangle.py:100-104),
+    with clipping off, and with culling off."""
+    W, H = 200, 136
+    view, proj = scenes.default_camera(W / H)
+    rng = np.random.default_rng(3)
+    tri = scenes.soup(3000, W, H, s=0.05, seed=5)
+    extra = np.array([
+        [[-9, -9, 0], [9, -9, 0], [0, 9, 0]],            # screen-filling, all vertices outside
+        [[-0.5, -0.5, 5], [0.5, -0.5, 5], [0, 0.5, 5]],  # behind the camera
+        [[-0.5, -0.5, 0], [0.5, -0.5, 4], [0, 0.5, 0]],  # crosses w = 0
+        [[0, 0, 0], [0, 0, 0], [0, 0, 0]],               # degenerate
+        [[np.nan, 0, 0], [1, 0, 0], [0, 1, 0]],          # NaN
+        [[np.inf, 0, 0], [1, 0, 0], [0, 1, 0]],          # inf
+        [[50, 50, 0], [51, 50, 0], [50, 51, 0]],         # far off-screen
+        [[-1, -1, 0.5], [1, -1, 0.5], [0, 1, 0.5]],      # big, front-facing
+        [[-1, -1, 0.2], [0, 1, 0.2], [1, -1, 0.2]],      # big, back-facing
+        [[1e-3, 0, 1], [2e-3, 0, 1], [1e-3, 1e-3, 1]],   # sub-pixel
+    ], dtype=np.float32)
+    tri = np.ascontiguousarray(np.concatenate([extra, tri, extra[::-1]]))
+    for culling in (True, False):
+        for clipping in (True, False):
+            scene = tina.Scene((W, H), culling=culling, clipping=clipping)
+            mesh = tina.SimpleMesh()
+            mesh.set_face_verts(tri)
+            scene.add_object(mesh)
+            scene.engine.set_camera(view, proj)
+            scene.render()
+            with np.errstate(all='ignore'):
+                ref = O.render_scene([(tri, None, None, tina.Diffuse())], W, H, view, proj, scene.lighting,
+                                     _flags(O, culling=culling, clipping=clipping))
+            import torch
+            torch.cuda.synchronize()
+            assert np.array_equal(scene.engine.depth.to_numpy(), ref['depth']), (culling, clipping)
+            assert np.array_equal(scene.triangle_raster.occup.to_numpy(), ref['occups'][-1]), (culling, clipping)
+            img, rimg = scene.img.to_numpy(), ref['image']
+            ok = np.isfinite(rimg)
+            assert np.array_equal(np.isfinite(img), ok)
+            assert np.abs(img[ok] - rimg[ok]).max() <= COLOR_TOL
+
+
+def test_empty_mesh_and_empty_scene(tina, O):
+    scene = tina.Scene((64, 48), bgcolor=[0.1, 0.2, 0.3])
+    scene.render()
+    img = scene.img.to_numpy()
+    assert np.allclose(img, O.tonemap(np.broadcast_to(np.float32([0.1, 0.2, 0.3]), (64, 48, 3))), atol=1e-6)
+    mesh = tina.SimpleMesh()
+    mesh.set_face_verts(np.zeros((0, 3, 3), np.float32))
+    scene.add_object(mesh)
+    scene.render()
+    assert (scene.engine.depth.to_numpy() == 2**30).all()
+    assert (scene.triangle_raster.occup.to_numpy() == -1).all()
+
+
+def test_multi_object_depth_carry_and_inter_object_ties(tina, O):
+    """Depth persists across objects, occup is per object; at exact inter-object depth ties the earlier
+    object keeps the pixel (strict `>` in triangle.py:123)."""
+    W, H = 160, 120
+    view, proj = scenes.default_camera(W / H)
+    a = scenes.soup(500, W, H, s=0.08, seed=1)
+    b = scenes.soup(500, W, H, s=0.08, seed=2)
+    objs = [(a, tina.Diffuse(color=[1, 0, 0])), (b, tina.Diffuse(color=[0, 1, 0])), (a.copy(), tina.Diffuse(color=[0, 0, 1]))]
+    scene = tina.Scene((W, H))
+    for tri, mat in objs:
+        m = tina.SimpleMesh()
+        m.set_face_verts(tri)
+        scene.add_object(m, mat)
+    scene.engine.set_camera(view, proj)
+    scene.render()
+    ref = O.render_scene([(t, None, None, m) for t, m in objs], W, H, view, proj, scene.lighting, _flags(O))
+    _check_frame(scene, ref)
+    assert (ref['occups'][-1] == -1).all()  # the third object is a copy of the first: it never wins (ties lose)
+
+
+def test_zero_copy_torch_inputs_and_direct_setters(tina, O):
+    """north_star: torch tensors accepted zero-copy; TriangleRaster.set_face_verts/norms fast path."""
+    import torch
+    W, H = 128, 96
+    view, proj = scenes.default_camera(W / H)
+    tri = scenes.soup(2000, W, H, s=0.03, seed=9)
+    nrm = np.random.default_rng(1).normal(size=tri.shape).astype(np.float32)
+    nrm /= np.linalg.norm(nrm, axis=2, keepdims=True)
+    engine = tina.Engine((W, H))
+    raster = tina.TriangleRaster(engine, smoothing=True)
+    tv, tn = torch.as_tensor(tri).cuda(), torch.as_tensor(nrm).cuda()
+    raster.set_face_verts(tv)
+    raster.set_face_norms(tn)
+    assert raster.verts.to_torch().data_ptr() == tv.data_ptr()  # aliased, not copied
+    engine.set_camera(view, proj)
+    engine.clear_depth()
+    raster.render_occup()
+    lighting = tina.Lighting()
+    lighting.add_light(dir=[1, 2, 3], color=[0.9, 0.9, 0.9])
+    lighting.set_ambient_light([0.1, 0.1, 0.1])
+    img = tina.Field(torch.zeros((W, H, 3), device='cuda'))
+    raster.render_color(tina.Shader(img, lighting, tina.Classic()))
+    ref = O.render_scene([(tri, nrm, None, tina.Classic())], W, H, view, proj, lighting, _flags(O, smoothing=True),
+                         do_tonemap=False)
+    torch.cuda.synchronize()
+    assert np.array_equal(raster.occup.to_numpy(), ref['occups'][0])
+    assert np.array_equal(engine.depth.to_numpy(), ref['depth'])
+    assert np.abs(img.to_numpy() - ref['image']).max() <= COLOR_TOL
+
+
+def test_transform_flip_and_smooth_normal_adapters(tina, O):
+    """MeshTransform / MeshFlipCulling / MeshFlipNormal over MeshModel (mesh/trans.py, mesh/cull.py)."""
+    W, H = 200, 200
+    obj = scenes.load_monkey()
+    trans = tina.translate([0.2, -0.1, 0.3]) @ tina.eularXYZ([0.3, 0.8, -0.2]) @ tina.scale([0.9, 1.1, 0.8])
+    view, proj = scenes.default_camera()
+    scene = tina.Scene((W, H), smoothing=True, texturing=True)
+    scene.add_object(tina.MeshFlipNormal(tina.MeshFlipCulling(tina.MeshTransform(tina.MeshModel(obj), trans))), tina.Classic())
+    scene.engine.set_camera(view, proj)
+    scene.render()
+    v, vn, vt = O.indexed(obj)
+    v, vn = O.transform(v, vn, trans)
+    v, vn, vt = v[:, ::-1].copy(), -vn[:, ::-1].copy(), vt[:, ::-1].copy()
+    ref = O.render_scene([(v, vn, vt, tina.Classic())], W, H, view, proj, scene.lighting,
+                         _flags(O, smoothing=True, texturing=True))
+    _check_frame(scene, ref)
+    assert np.array_equal(scene.triangle_raster.verts.to_numpy(), v)
+    assert np.array_equal(scene.triangle_raster.norms.to_numpy(), vn)
+    assert np.array_equal(scene.triangle_raster.coors.to_numpy(), vt)
+
+
+def test_maxfaces_overflow_raises(tina):
+    scene = tina.Scene((32, 32), maxfaces=10)
+    m = tina.SimpleMesh()
+    m.set_face_verts(np.zeros((11, 3, 3), np.float32))
+    scene.add_object(m)
+    with pytest.raises(ValueError):
+        scene.render()
+
+
+def test_c2_full_size_bit_exact(tina, O):
+    """C2 at BASELINE size: MeshGrid(1024) wave, 2,093,058 faces, 1920x1080, smooth + Classic."""
+    n, W, H = 1024, 1920, 1080
+    pos = scenes.wave_grid_pos(n)
+    scene = tina.Scene((W, H), smoothing=True, maxfaces=2**21)
+    grid = tina.MeshGrid(n)
+    grid.pos.from_numpy(pos)
+    scene.add_object(grid, tina.Classic())
+    view, proj = scenes.default_camera(W / H)
+    scene.engine.set_camera(view, proj)
+    scene.render()
+    fv, fn = O.grid_faces(pos), O.grid_faces(O.grid_normals(pos))
+    ref = O.render_scene([(fv, fn, None, tina.Classic())], W, H, view, proj, scene.lighting, _flags(O, smoothing=True))
+    _check_frame(scene, ref)
