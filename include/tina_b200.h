@@ -152,12 +152,16 @@ int tina_raster_occup(TinaRaster *r, int32_t *occup, void *stream);
 /* device views of the current object's attribute buffers (may be NULL) */
 int tina_raster_buffers(TinaRaster *r, const float **verts, const float **norms, const float **coors,
                         int64_t *nfaces);
-/* strategy knobs; which: 0 = max bbox area rasterised per thread, 1 = max bbox area
- * rasterised per warp, 2 = force every face through the binned tile path */
+/* strategy knobs; which: 0 = max bbox area rasterised per thread in the setup kernel,
+ * 2 = force every face through the binned tile path, 3 = collect stats, 4 = record CUDA
+ * events around every kernel (read back with tina_raster_kernel_times) */
 int tina_raster_set_tuning(TinaRaster *r, int which, int value);
 /* counters of the last render_occup (synchronises): faces culled, clipped, per-thread,
  * per-warp, queued for the tile path, tile-list entries */
 int tina_raster_stats(TinaRaster *r, int64_t *out6_host);
+/* ms of the last launch of: setup+raster, bin count, bin scatter, tile raster, render_color
+ * (-1 = never recorded); needs tuning knob 4; synchronises on the recorded events */
+int tina_raster_kernel_times(TinaRaster *r, float *ms5_host);
 
 /* ---- frame glue (scene/raster.py:176,202-203) -------------------------------- */
 int tina_image_fill(float *image, int64_t npixels, const float *rgb_host, void *stream);

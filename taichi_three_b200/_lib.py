@@ -62,6 +62,7 @@ SIGNATURES = {
     'tina_raster_buffers': (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i64)]),
     'tina_raster_set_tuning': (_i, [_vp, _i, _i]),
     'tina_raster_stats': (_i, [_vp, C.POINTER(_i64)]),
+    'tina_raster_kernel_times': (_i, [_vp, _fp]),
     'tina_image_fill': (_i, [_vp, _i64, _fp, _vp]),
     'tina_image_tonemap': (_i, [_vp, _i64, _vp]),
 }

@@ -178,7 +178,13 @@ class TriangleRaster:
         _, _, t, nf = self._buffers()
         return Field(wrap_device(t, (nf, 3, 2), torch.float32, self.engine.device, owner=self))
 
-    def set_tuning(self, tiny_max=None, force_tiles=None, collect_stats=None):
+    def kernel_times(self):
+        """ms of the last launch of each kernel (needs set_tuning(profile=1)); -1 = not recorded."""
+        out = (C.c_float * 5)()
+        _lib.check(_lib.lib().tina_raster_kernel_times(self._h, out))
+        return dict(zip(('raster_faces', 'bin_count', 'bin_scatter', 'tile_raster', 'render_color'), list(out)))
+
+    def set_tuning(self, tiny_max=None, force_tiles=None, collect_stats=None, profile=None):
         """Strategy knobs (every setting produces identical bits): max bbox area rasterised per
         thread in the setup kernel; force every face through the binned tile path."""
         L = _lib.lib()
@@ -188,6 +194,8 @@ class TriangleRaster:
             _lib.check(L.tina_raster_set_tuning(self._h, 2, int(force_tiles)))
         if collect_stats is not None:
             _lib.check(L.tina_raster_set_tuning(self._h, 3, int(collect_stats)))
+        if profile is not None:
+            _lib.check(L.tina_raster_set_tuning(self._h, 4, int(profile)))
 
     def stats(self):
         out = (C.c_int64 * 6)()
