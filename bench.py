@@ -366,7 +366,7 @@ def run_ours(args):
             'cpu_baseline': cpu,
             'e2e': {'value': e2e_value, 'unit': 'Mtris/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'ms_per_step': float(e2e_s.item()) * 1e3, 'steps': Ke, 'image_checksum': checksum},
-            'gpu_launches': 5 * K,
+            'gpu_launches': 4 * K,  # k_clear_keys, k_raster_faces, k_large_path, k_render_color
             'clocks': clocks,
         }
         print(json.dumps(line), flush=True)

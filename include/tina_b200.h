@@ -152,15 +152,18 @@ int tina_raster_occup(TinaRaster *r, int32_t *occup, void *stream);
 /* device views of the current object's attribute buffers (may be NULL) */
 int tina_raster_buffers(TinaRaster *r, const float **verts, const float **norms, const float **coors,
                         int64_t *nfaces);
-/* strategy knobs; which: 0 = max bbox area rasterised per thread in the setup kernel,
- * 2 = force every face through the binned tile path, 3 = collect stats, 4 = record CUDA
- * events around every kernel (read back with tina_raster_kernel_times) */
+/* strategy knobs (every setting yields identical bits); which:
+ * 0 = most candidate pixels a face may have to be rasterised per thread in the setup kernel,
+ * 2 = force every face through the tile path, 3 = collect stats, 4 = record CUDA events around
+ * every kernel (tina_raster_kernel_times), 5 = candidate tightening on/off, 6 = read the key
+ * before the atomicMin on/off, 7 = largest queue the tile path handles without binning,
+ * 8 = always interpret the material program (no specialised shading kernels) */
 int tina_raster_set_tuning(TinaRaster *r, int which, int value);
 /* counters of the last render_occup (synchronises): faces culled, clipped, per-thread,
  * per-warp, queued for the tile path, tile-list entries */
 int tina_raster_stats(TinaRaster *r, int64_t *out6_host);
-/* ms of the last launch of: setup+raster, bin count, bin scatter, tile raster, render_color
- * (-1 = never recorded); needs tuning knob 4; synchronises on the recorded events */
+/* ms of the last launch of: [0] k_raster_faces, [3] k_large_path, [4] k_render_color
+ * ([1], [2] unused; -1 = never recorded); needs tuning knob 4; synchronises on the events */
 int tina_raster_kernel_times(TinaRaster *r, float *ms5_host);
 
 /* ---- frame glue (scene/raster.py:176,202-203) -------------------------------- */

@@ -300,9 +300,79 @@ def flatten_material(material):
     return out[0], out[1], out[2], P.textures
 
 
-def material_struct(material, device):
+_F = np.float32
+_INV_PI = _F(0.3183098861837907)  # Python folds `1 / ti.pi` in f64 (material.py:393), stored as f32
+
+
+def fold_program(code):
+    """Constant-fold a postfix program on the host with numpy f32 arithmetic in exactly the
+    op order of the device VM (IEEE, no contraction => same bits as evaluating per pixel).
+    `Input('color')` is the constant (1, 1, 1) on the raster path (triangle.py:48)."""
+    stack = []  # items: ('c', f32[3]) constant | ('d', [instr, ...]) dynamic sub-program
+
+    def code_of(item):
+        return [(_lib.OP_CONST, 0, tuple(float(x) for x in item[1]))] if item[0] == 'c' else item[1]
+
+    def push_dyn(operands, instr):
+        seq = []
+        for o in operands:
+            seq += code_of(o)
+        stack.append(('d', seq + [instr]))
+
+    for op, arg, c in code:
+        ins = (op, arg, c)
+        if op == _lib.OP_CONST:
+            stack.append(('c', np.asarray(c, dtype=_F)))
+        elif op == _lib.OP_INPUT:
+            if arg == 1:
+                stack.append(('c', np.ones(3, dtype=_F)))
+            else:
+                stack.append(('d', [ins]))
+        elif op == _lib.OP_LAMBERT:
+            stack.append(('c', np.full(3, _INV_PI, dtype=_F)))
+        elif op == _lib.OP_TEXTURE:
+            push_dyn([stack.pop()], ins)
+        elif op == _lib.OP_PHONG:
+            push_dyn([stack.pop()], ins)
+        elif op == _lib.OP_COOK:
+            f0, ro = stack.pop(), stack.pop()
+            push_dyn([ro, f0], ins)
+        elif op == _lib.OP_FRESNEL:
+            sp, al, me = stack.pop(), stack.pop(), stack.pop()
+            if sp[0] == al[0] == me[0] == 'c':
+                m, a, s_ = me[1], al[1], sp[1]
+                stack.append(('c', m * a + (_F(1) - m) * _F(0.16) * (s_ * s_)))
+            else:
+                push_dyn([me, al, sp], ins)
+        elif op == _lib.OP_MIX:
+            b, a, f = stack.pop(), stack.pop(), stack.pop()
+            if b[0] == a[0] == f[0] == 'c':
+                stack.append(('c', (_F(1) - f[1]) * a[1] + f[1] * b[1]))
+            else:
+                push_dyn([f, a, b], ins)
+        elif op == _lib.OP_MUL:
+            w, f = stack.pop(), stack.pop()
+            if w[0] == f[0] == 'c':
+                stack.append(('c', f[1] * w[1]))
+            else:
+                push_dyn([f, w], ins)
+        elif op == _lib.OP_ADD:
+            b, a = stack.pop(), stack.pop()
+            if b[0] == a[0] == 'c':
+                stack.append(('c', a[1] + b[1]))
+            else:
+                push_dyn([a, b], ins)
+        else:
+            raise ValueError(op)
+    assert len(stack) == 1, 'malformed material program'
+    return code_of(stack[0])
+
+
+def material_struct(material, device, fold=True):
     """Build the TinaMaterial POD; returns (struct, keepalive list of device tensors)."""
     brdf, amb, emi, textures = flatten_material(material)
+    if fold:
+        brdf, amb, emi = fold_program(brdf), fold_program(amb), fold_program(emi)
     m = _lib.TinaMaterial()
     m.n_brdf, m.n_ambient, m.n_emission, m.ntex = len(brdf), len(amb), len(emi), len(textures)
     keep = []

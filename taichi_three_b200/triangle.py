@@ -182,11 +182,16 @@ class TriangleRaster:
         """ms of the last launch of each kernel (needs set_tuning(profile=1)); -1 = not recorded."""
         out = (C.c_float * 5)()
         _lib.check(_lib.lib().tina_raster_kernel_times(self._h, out))
-        return dict(zip(('raster_faces', 'bin_count', 'bin_scatter', 'tile_raster', 'render_color'), list(out)))
+        return dict(zip(('raster_faces', 'unused1', 'unused2', 'large_path', 'render_color'), list(out)))
 
-    def set_tuning(self, tiny_max=None, force_tiles=None, collect_stats=None, profile=None):
-        """Strategy knobs (every setting produces identical bits): max bbox area rasterised per
-        thread in the setup kernel; force every face through the binned tile path."""
+    def set_tuning(self, tiny_max=None, force_tiles=None, collect_stats=None, profile=None, tighten=None,
+                   precheck=None, scan_max=None, generic_vm=None):
+        """Strategy knobs (every setting produces identical bits): tiny_max = most candidate pixels a
+        face may have to be rasterised per thread in the setup kernel (more -> tile path);
+        force_tiles = every face through the tile path; tighten = skip bbox pixels whose sample
+        provably fails (0 = walk the full reference bbox); precheck = read the key before the
+        atomicMin; scan_max = largest queue the tile path handles without binning;
+        generic_vm = always interpret the material program."""
         L = _lib.lib()
         if tiny_max is not None:
             _lib.check(L.tina_raster_set_tuning(self._h, 0, int(tiny_max)))
@@ -196,8 +201,11 @@ class TriangleRaster:
             _lib.check(L.tina_raster_set_tuning(self._h, 3, int(collect_stats)))
         if profile is not None:
             _lib.check(L.tina_raster_set_tuning(self._h, 4, int(profile)))
+        for which, v in ((5, tighten), (6, precheck), (7, scan_max), (8, generic_vm)):
+            if v is not None:
+                _lib.check(L.tina_raster_set_tuning(self._h, which, int(v)))
 
     def stats(self):
         out = (C.c_int64 * 6)()
         _lib.check(_lib.lib().tina_raster_stats(self._h, out))
-        return dict(zip(('culled', 'clipped', 'direct', 'warp', 'queued', 'tile_entries'), list(out)))
+        return dict(zip(('culled', 'clipped', 'survivors', 'unused', 'queued', 'tile_entries'), list(out)))

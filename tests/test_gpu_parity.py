@@ -263,3 +263,140 @@ def test_c2_full_size_bit_exact(tina, O):
     fv, fn = O.grid_faces(pos), O.grid_faces(O.grid_normals(pos))
     ref = O.render_scene([(fv, fn, None, tina.Classic())], W, H, view, proj, scene.lighting, _flags(O, smoothing=True))
     _check_frame(scene, ref)
+
+
+def _keys(scene):
+    import torch
+    torch.cuda.synchronize()
+    return scene.engine.keys.cpu().numpy().copy()
+
+
+def _adversarial_triangles(rng, n, W, H, view, proj):
+    """Screen-space recipes aimed at the candidate-tightening guards: sub-pixel triangles whose
+    vertices sit within 1e-3..1e-1 px of sample centres, needles / slivers pointing at samples,
+    near-degenerate areas, triangles hugging the guard thresholds -- unprojected to world space."""
+    W2V = np.asarray(proj, np.float64) @ np.asarray(view, np.float64)
+    V2W = np.linalg.inv(W2V)
+    kind = rng.integers(0, 6, n)
+    cx = rng.integers(2, W - 2, n) + 0.5
+    cy = rng.integers(2, H - 2, n) + 0.5
+    ang = rng.uniform(0, 2 * np.pi, (n, 3))
+    rad = np.empty((n, 3))
+    off = np.zeros((n, 2))
+    # 0: tiny around a sample; 1: tiny just beside a sample; 2: needle pointing at a sample;
+    # 3: sliver across a sample; 4: ~1-3 px ordinary; 5: near-collinear
+    rad[:] = rng.uniform(0.05, 0.6, (n, 3))
+    m = kind == 1
+    off[m] = rng.choice([-1, 1], (m.sum(), 2)) * 10.0 ** rng.uniform(-3, -0.5, (m.sum(), 2)) + rng.uniform(0.3, 0.7, (m.sum(), 2)) * rng.choice([-1, 1], (m.sum(), 2))
+    m = kind == 4
+    rad[m] = rng.uniform(0.5, 3.0, (m.sum(), 3))
+    pts = np.stack([cx[:, None] + off[:, :1] + rad * np.cos(ang), cy[:, None] + off[:, 1:] + rad * np.sin(ang)], axis=2)
+    m = kind == 2  # needle: two vertices far away and close together, tip near the sample
+    k = m.sum()
+    d = rng.uniform(0, 2 * np.pi, k)
+    ln = rng.uniform(1.0, 6.0, k)
+    wdt = 10.0 ** rng.uniform(-4, -1, k)
+    tip = np.stack([cx[m], cy[m]], 1) + rng.normal(0, 1, (k, 2)) * 10.0 ** rng.uniform(-4, -1, (k, 1))
+    dirv = np.stack([np.cos(d), np.sin(d)], 1)
+    nrm = np.stack([-np.sin(d), np.cos(d)], 1)
+    pts[m, 0] = tip
+    pts[m, 1] = tip + dirv * ln[:, None] + nrm * wdt[:, None]
+    pts[m, 2] = tip + dirv * ln[:, None] - nrm * wdt[:, None]
+    m = kind == 3  # sliver through the sample
+    k = m.sum()
+    d = rng.uniform(0, 2 * np.pi, k)
+    dirv = np.stack([np.cos(d), np.sin(d)], 1)
+    nrm = np.stack([-np.sin(d), np.cos(d)], 1)
+    c0 = np.stack([cx[m], cy[m]], 1) + nrm * (rng.normal(0, 1, (k, 1)) * 10.0 ** rng.uniform(-5, -1, (k, 1)))
+    ln = rng.uniform(0.5, 4.0, (k, 1))
+    pts[m, 0] = c0 - dirv * ln
+    pts[m, 1] = c0 + dirv * ln
+    pts[m, 2] = c0 + dirv * rng.uniform(-1, 1, (k, 1)) * ln + nrm * 10.0 ** rng.uniform(-5, -1, (k, 1))
+    m = kind == 5
+    k = m.sum()
+    pts[m, 2] = 0.5 * (pts[m, 0] + pts[m, 1]) + rng.normal(0, 1, (k, 2)) * 10.0 ** rng.uniform(-7, -2, (k, 1))
+    # random winding, then unproject at random depths
+    flip = rng.random(n) < 0.3
+    pts[flip] = pts[flip][:, [0, 2, 1]]
+    ndc = np.empty((n, 3, 4))
+    ndc[..., 0] = pts[..., 0] / W * 2 - 1
+    ndc[..., 1] = pts[..., 1] / H * 2 - 1
+    dist = rng.uniform(1.0, 6.0, (n, 3))
+    ndc[..., 2] = (proj[2, 2] * (-dist) + proj[2, 3]) / dist
+    ndc[..., 3] = 1
+    wp = ndc @ V2W.T
+    return np.ascontiguousarray((wp[..., :3] / wp[..., 3:4]).astype(np.float32))
+
+
+@pytest.mark.parametrize('seed,bias', [(1, (0.5, 0.5)), (2, (0.5, 0.5)), (3, (0.123, 0.877)), (4, (0.0, 1.0))])
+def test_tightening_is_exact(tina, O, seed, bias):
+    """Candidate tightening (k_raster_faces phase A) must never drop a pixel the reference accepts:
+    tightened == untightened key buffers on adversarial triangle sets, and == the oracle."""
+    W, H, n = 256, 192, 400000
+    view, proj = scenes.default_camera(W / H)
+    tri = _adversarial_triangles(np.random.default_rng(seed), n, W, H, view, proj)
+    out = []
+    for culling in (True, False):
+        for tighten in (1, 0):
+            scene = tina.Scene((W, H), maxfaces=n, culling=culling)
+            mesh = tina.SimpleMesh(maxfaces=n)
+            mesh.set_face_verts(tri)
+            scene.add_object(mesh)
+            scene.engine.set_camera(view, proj)
+            scene.engine.bias[None] = bias
+            scene.triangle_raster.set_tuning(tighten=tighten, tiny_max=64)
+            scene.render()
+            out.append(_keys(scene))
+        assert np.array_equal(out[-1], out[-2]), f'tightening changed {(out[-1] != out[-2]).sum()} keys (culling={culling})'
+    occup, depth, _, st = O.render_occup(tri, (proj @ view).astype(np.float32), W, H, O.CULLING | O.CLIPPING, bias=bias)
+    assert np.array_equal(out[0] >> 32, depth.astype(np.int64))
+    assert np.array_equal((out[0] & 0xffffffff) - 1, occup.astype(np.int64))
+    assert st['covered'] > 10000
+
+
+def test_tile_path_modes_agree(tina, O):
+    """Small queues are rasterised by per-tile bbox scanning, large ones through the binned lists
+    (count -> prefix sum -> scatter); list overflow falls back to scanning.  All identical."""
+    W, H = 384, 256
+    view, proj = scenes.default_camera(W / H)
+    tri = scenes.soup(1500, W, H, s=0.12, seed=21)  # medium/large triangles
+    ref = None
+    for tuning in (dict(), dict(scan_max=0), dict(scan_max=100000), dict(force_tiles=1, scan_max=0), dict(tiny_max=0, scan_max=1)):
+        scene = _render_soup(tina, tri, W, H, view, proj, **tuning)
+        k = _keys(scene)
+        if ref is None:
+            ref = k
+            r = O.render_scene([(tri, None, None, tina.Diffuse())], W, H, view, proj, scene.lighting, _flags(O))
+            _check_frame(scene, r)
+        assert np.array_equal(k, ref), tuning
+
+
+def test_specialised_shading_equals_interpreter(tina, O):
+    """The Diffuse / Classic / PBR shading kernels and the host constant folding give the same
+    bits as interpreting the unfolded material program."""
+    import torch
+    W, H = 160, 120
+    view, proj = scenes.default_camera(W / H)
+    tri = scenes.soup(800, W, H, s=0.1, seed=5)
+    nrm = np.random.default_rng(2).normal(size=tri.shape).astype(np.float32)
+    nrm /= np.linalg.norm(nrm, axis=2, keepdims=True)
+    mats = [tina.Diffuse(), tina.Diffuse(color=[0.2, 0.5, 0.9]), tina.Classic(), tina.Classic(color=[0.9, 0.3, 0.1], shineness=8, specular=0.7),
+            tina.PBR(basecolor=[0.8, 0.7, 0.6], metallic=0.9, roughness=0.05), tina.PBR(),
+            tina.Lambert() * [1, 0, 0] + tina.Emission() * 0.25 + tina.Phong(shineness=[4, 16, 64]) * 0.3]
+    for mat in mats:
+        imgs = []
+        for generic in (0, 1):
+            scene = tina.Scene((W, H), smoothing=True, tonemap=False)
+            mesh = tina.SimpleMesh()
+            mesh.set_face_verts(tri)
+            mesh.set_face_norms(nrm)
+            scene.add_object(mesh, mat)
+            scene.engine.set_camera(view, proj)
+            scene.lighting.add_light(pos=[0.5, 0.5, 2.0], color=[0.3, 0.6, 0.9])
+            scene.triangle_raster.set_tuning(generic_vm=generic)
+            scene.render()
+            torch.cuda.synchronize()
+            imgs.append(scene.img.to_numpy())
+        assert np.array_equal(imgs[0], imgs[1])
+        ref = O.render_scene([(tri, nrm, None, mat)], W, H, view, proj, scene.lighting, _flags(O, smoothing=True), do_tonemap=False)
+        assert np.abs(imgs[0] - ref['image']).max() <= COLOR_TOL
