@@ -47,6 +47,16 @@ class Lighting:
         self.ambient_color[None] = np.array(color, dtype=np.float32)
 
     def struct(self):
+        """TinaLighting POD, rebuilt only when the light state changed."""
+        key = (self.light_dirs.tobytes(), self.light_colors.tobytes(), self.ambient_color.to_numpy().tobytes(),
+               int(self.nlights[None]))
+        if getattr(self, '_cache_key', None) == key:
+            return self._cache_struct
+        L = self._build_struct()
+        self._cache_key, self._cache_struct = key, L
+        return L
+
+    def _build_struct(self):
         L = _lib.TinaLighting()
         n = int(self.nlights[None])
         L.nlights = n

@@ -368,6 +368,28 @@ def fold_program(code):
     return code_of(stack[0])
 
 
+def _walk(node, seen):
+    if id(node) in seen or not isinstance(node, Node):
+        return
+    seen[id(node)] = node
+    for child in getattr(node, 'params', {}).values():
+        _walk(child, seen)
+    for attr in ('mat', 'mat1', 'mat2'):
+        if hasattr(node, attr):
+            _walk(getattr(node, attr), seen)
+
+
+def param_signature(material):
+    """Values of every runtime Param in the graph (cheap after the first call: the node list is cached)."""
+    params = material.__dict__.get('_tina_params')
+    if params is None:
+        seen = {}
+        _walk(material, seen)
+        params = [n for n in seen.values() if isinstance(n, Param)]
+        material.__dict__['_tina_params'] = params
+    return tuple(p._value.tobytes() for p in params)
+
+
 def material_struct(material, device, fold=True):
     """Build the TinaMaterial POD; returns (struct, keepalive list of device tensors)."""
     brdf, amb, emi, textures = flatten_material(material)

@@ -135,13 +135,26 @@ class TriangleRaster:
             img = s.img.to_torch() if hasattr(s.img, 'to_torch') else s.img
             if img.dtype != torch.float32 or not img.is_contiguous() or img.numel() != self.res[0] * self.res[1] * 3:
                 raise ValueError('shader image must be a contiguous float32 [W, H, 3] CUDA tensor')
-            mat, keep = material_struct(s.material, self.engine.device)
+            mat, keep = self._material_struct(s.material)
             light = s.lighting.struct()
             flags = (_lib.TINA_COLOR_TONEMAP if tonemap else 0) | (_lib.TINA_COLOR_FILL_BG if fill_bg is not None else 0)
             bg = _fp(np.broadcast_to(np.asarray(fill_bg if fill_bg is not None else 0, dtype=np.float32), (3,)))
             _lib.check(_lib.lib().tina_raster_render_color(self._h, C.byref(mat), C.byref(light), C.c_void_p(img.data_ptr()),
                                                            flags, bg, _stream()))
             self._mat_keep = keep
+
+    def _material_struct(self, material):
+        """Flattening + folding is pure host work: cache it per material object, keyed by the
+        current values of its runtime Param nodes (matr/nodes.py:52-76)."""
+        from .material import param_signature
+        cache = self.__dict__.setdefault('_mat_cache', {})
+        sig = param_signature(material)
+        hit = cache.get(id(material))
+        if hit is None or hit[0] != sig or hit[3] is not material:
+            mat, keep = material_struct(material, self.engine.device)
+            hit = (sig, mat, keep, material)
+            cache[id(material)] = hit
+        return hit[1], hit[2]
 
     # ---- public state ------------------------------------------------------------------
     @property
