@@ -1,0 +1,190 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz by running the REFERENCE'S OWN SOURCES (/root/reference/tina, unmodified)
+under the f32 NumPy emulation of the Taichi runtime in oracle/ref_shim (taichi itself cannot be
+installed here).  Run in the build container only:  python tests/golden/make_golden.py
+
+Each file holds, per object, the face arrays the reference's set_object produced
+(raster.verts / norms / coors), the camera (W2V, V2W, bias), lights, a material spec string for
+this repo's material classes, and the reference's outputs: per-object occup, final depth,
+pre-tonemap image, final image (Scene.img).
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+REF = '/root/reference'
+
+from oracle import ref_shim  # noqa: E402
+
+tina = ref_shim.load_tina(REF)
+
+
+def render_and_dump(name, scene, specs, textures=()):
+    """Replays Scene.render (scene/raster.py:168-207) step by step to capture per-object state."""
+    eng = scene.engine
+    scene.image.fill(scene.bgcolor)
+    eng.clear_depth()
+    out = {'res': np.array(scene.res.entries if hasattr(scene.res, 'entries') else scene.res, dtype=np.int32),
+           'W2V': eng.W2V.to_numpy().astype(np.float32), 'V2W': eng.V2W.to_numpy().astype(np.float32),
+           'bias': eng.bias.to_numpy().astype(np.float32), 'bgcolor': np.float32(scene.bgcolor),
+           'nobjects': np.int32(len(scene.objects))}
+    L = scene.lighting
+    nl = int(L.nlights[None])
+    out['light_dirs'] = L.light_dirs.to_numpy()[:nl].astype(np.float32)
+    out['light_colors'] = L.light_colors.to_numpy()[:nl].astype(np.float32)
+    out['ambient'] = L.ambient_color.to_numpy().astype(np.float32)
+    for k, (obj, oinfo) in enumerate(scene.objects.items()):
+        r = oinfo.raster
+        r.set_object(obj)
+        r.render_occup()
+        r.render_color(scene.shaders[oinfo.material])
+        n = int(r.nfaces[None])
+        out[f'verts{k}'] = r.verts.to_numpy()[:n].astype(np.float32)
+        if r.smoothing:
+            out[f'norms{k}'] = r.norms.to_numpy()[:n].astype(np.float32)
+        if r.texturing:
+            out[f'coors{k}'] = r.coors.to_numpy()[:n].astype(np.float32)
+        out[f'occup{k}'] = r.occup.to_numpy().astype(np.int32)
+        out[f'material{k}'] = np.array(specs[k])
+        out['flags'] = np.int32((1 if r.smoothing else 0) | (2 if r.texturing else 0) | (4 if r.culling else 0) |
+                                (8 if r.clipping else 0))
+    out['depth'] = eng.depth.to_numpy().astype(np.int32)
+    out['image_pre_tonemap'] = scene.image.to_numpy().astype(np.float32)
+    if scene.tonemap:
+        scene.tonemap.apply(scene.image)
+    out['image'] = scene.img.to_numpy().astype(np.float32)
+    for i, t in enumerate(textures):
+        out[f'tex{i}'] = np.asarray(t)
+    path = os.path.join(HERE, name + '.npz')
+    np.savez_compressed(path, **out)
+    cov = int((out['depth'] < 2**30).sum())
+    print(f'{name}: {out["res"].tolist()} objects={len(scene.objects)} covered={cov} -> {os.path.getsize(path)} B')
+
+
+def camera(scene, aspect, back=(0, 0, 3), pos=(0, 0, 0), fov=60):
+    scene.engine.set_camera(tina.lookat(pos=pos, back=back), tina.perspective(fov, aspect))
+
+
+def case_monkey():
+    scene = tina.Scene((96, 96))
+    scene.add_object(tina.MeshModel(os.path.join(REF, 'assets/monkey.obj')))
+    camera(scene, 1.0)
+    render_and_dump('monkey_flat_diffuse', scene, ['Diffuse()'])
+
+
+def case_grid():
+    scene = tina.Scene((80, 60), smoothing=True)
+    mesh = tina.MeshGrid(14)
+    pos = mesh.pos.to_numpy()
+    xy = pos[..., :2].astype(np.float64)
+    pos[..., 2] = (0.1 * np.sin(10 * np.sqrt((xy**2).sum(-1)) - 2 * np.pi * 0.25)).astype(np.float32)
+    mesh.pos.from_numpy(pos)
+    scene.add_object(tina.MeshNoCulling(mesh), tina.Classic())
+    camera(scene, 80 / 60, back=(1.0, 1.5, 2.5))
+    render_and_dump('grid_wave_nocull_smooth_classic', scene, ['Classic()'])
+    np.save(os.path.join(HERE, 'grid_wave_pos.npy'), pos)
+
+
+def case_cornell():
+    import taichi_three_b200 as mine
+    scene = tina.Scene((64, 64), smoothing=True, texturing=True)
+    scene.load_gltf(os.path.join(REF, 'assets/cornell.gltf'))
+    view, proj = mine.orbit_camera(center=(0, 2, 0), radius=6.0, theta=0.2, phi=0.7)
+    scene.engine.set_camera(view, proj)
+    g = tina.readgltf(os.path.join(REF, 'assets/cornell.gltf'))
+    specs = ['PBR(basecolor=[0.8, 0.8, 0.8], metallic=M0, roughness=R0)'] * 2 + ['PBR(basecolor=Texture(tex0), metallic=M1, roughness=R1)']
+    # exact factors straight from the file
+    import json
+    root = json.load(open(os.path.join(REF, 'assets/cornell.gltf')))
+    m0, m1 = (m['pbrMetallicRoughness'] for m in root['materials'][:2])
+    specs = [f"PBR(basecolor={m0['baseColorFactor'][:3]!r}, metallic={m0['metallicFactor']!r}, roughness={m0['roughnessFactor']!r})"] * 2
+    specs.append(f"PBR(basecolor=Texture(tex0), metallic={m1['metallicFactor']!r}, roughness={m1['roughnessFactor']!r})")
+    from PIL import Image
+    import base64
+    import io
+    uri = root['images'][0].get('uri')
+    if uri is None:
+        bv = root['bufferViews'][root['images'][0]['bufferView']]
+        buf = base64.b64decode(root['buffers'][bv['buffer']]['uri'].split('base64,')[1])
+        data = buf[bv['byteOffset']:bv['byteOffset'] + bv['byteLength']]
+    else:
+        data = base64.b64decode(uri.split('base64,')[1])
+    tex = np.swapaxes(np.array(Image.open(io.BytesIO(data))), 0, 1)
+    render_and_dump('cornell_pbr_textured', scene, specs, textures=[tex])
+
+
+EDGE = np.array([
+    [[-9, -9, 0], [9, -9, 0], [0, 9, 0]],            # screen-filling, every vertex outside the NDC cube
+    [[-0.5, -0.5, 5], [0.5, -0.5, 5], [0, 0.5, 5]],  # behind the camera
+    [[-0.5, -0.5, 0], [0.5, -0.5, 4], [0, 0.5, 0]],  # crosses w = 0
+    [[0, 0, 0], [0, 0, 0], [0, 0, 0]],               # degenerate
+    [[np.nan, 0, 0], [1, 0, 0], [0, 1, 0]],          # NaN
+    [[50, 50, 0], [51, 50, 0], [50, 51, 0]],         # far off-screen
+    [[-1, -1, 0.5], [1, -1, 0.5], [0, 1, 0.5]],      # big, front-facing
+    [[-1, -1, 0.2], [0, 1, 0.2], [1, -1, 0.2]],      # big, back-facing
+    [[-0.8, -0.8, 0.8], [0.2, -0.8, 0.8], [-0.8, 0.2, 0.8]],  # overlaps, nearer
+    [[1e-3, 0, 1], [2e-3, 0, 1], [1e-3, 1e-3, 1]],   # sub-pixel
+    [[-1.2, 0.3, 0.1], [1.2, 0.3, 0.1], [0.0, 0.35, 0.1]],    # sliver across the screen
+], dtype=np.float32)
+
+
+def case_edges():
+    import scenes
+    soup = scenes.soup(60, 40, 28, s=0.1, seed=5)
+    tri = np.ascontiguousarray(np.concatenate([EDGE, soup, EDGE[::-1]]))
+    for culling in (True, False):
+        for clipping in (True, False):
+            scene = tina.Scene((40, 28), culling=culling, clipping=clipping, maxfaces=len(tri))
+            mesh = tina.SimpleMesh(maxfaces=len(tri))
+            with np.errstate(all='ignore'):
+                mesh.set_face_verts(tri)
+                scene.add_object(mesh)
+                camera(scene, 40 / 28)
+                render_and_dump(f'edges_cull{int(culling)}_clip{int(clipping)}', scene, ['Diffuse()'])
+
+
+def case_multi_object():
+    import scenes
+    a = scenes.soup(40, 48, 36, s=0.12, seed=1)
+    b = scenes.soup(40, 48, 36, s=0.12, seed=2)
+    scene = tina.Scene((48, 36), maxfaces=64, bgcolor=0.25)
+    specs = ['Diffuse(color=[1.0, 0.2, 0.1])', 'Classic(color=[0.1, 0.9, 0.2], shineness=8, specular=0.6)', 'Diffuse(color=[0.1, 0.2, 1.0])']
+    mats = [tina.Diffuse(color=[1.0, 0.2, 0.1]), tina.Classic(color=[0.1, 0.9, 0.2], shineness=8, specular=0.6),
+            tina.Diffuse(color=[0.1, 0.2, 1.0])]
+    for tri, mat in zip((a, b, a.copy()), mats):
+        m = tina.SimpleMesh(maxfaces=64)
+        m.set_face_verts(tri)
+        scene.add_object(m, mat)
+    camera(scene, 48 / 36)
+    scene.engine.bias[None] = [0.3, 0.8]  # engine.py:31-39 jittered sample position
+    render_and_dump('multi_object_ties_bias', scene, specs)
+
+
+def case_lights_materials():
+    scene = tina.Scene((56, 56), smoothing=True, texturing=True)
+    obj = tina.readobj(os.path.join(REF, 'assets/monkey.obj'))
+    trans = tina.translate([0.2, -0.1, 0.3]) @ tina.eularXYZ([0.3, 0.8, -0.2]) @ tina.scale([0.9, 1.1, 0.8])
+    mesh = tina.MeshFlipNormal(tina.MeshFlipCulling(tina.MeshTransform(tina.MeshModel(obj), trans)))
+    mat = tina.Lambert() * [0.8, 0.5, 0.3] + tina.Emission() * 0.05 + tina.Phong(shineness=12) * 0.3
+    scene.add_object(mesh, mat)
+    scene.lighting.add_light(pos=[0.5, 0.8, 2.0], color=[0.3, 0.6, 0.9])
+    scene.lighting.add_light(dir=[-1, 0.2, 0.5], color=[0.4, 0.1, 0.1])
+    camera(scene, 1.0, back=(0.5, 0.3, 2.8))
+    render_and_dump('monkey_transform_flip_lights_addmaterial', scene,
+                    ['Lambert() * [0.8, 0.5, 0.3] + Emission() * 0.05 + Phong(shineness=12) * 0.3'])
+    np.save(os.path.join(HERE, 'monkey_trans.npy'), trans)
+
+
+if __name__ == '__main__':
+    np.seterr(all='ignore')
+    case_monkey()
+    case_grid()
+    case_cornell()
+    case_edges()
+    case_multi_object()
+    case_lights_materials()

@@ -1,0 +1,117 @@
+"""Pins the CPU oracle (oracle/tina_oracle.c) -- and the host-side mesh providers / loaders -- against
+golden vectors produced by the REFERENCE'S OWN SOURCES executed under oracle/ref_shim
+(tests/golden/make_golden.py; taichi itself is not installable here).
+
+  face ids (occup) and integer depth: bit-exact
+  colour: <= 2e-6 abs (pre-tonemap and final); the residue is Python-scope f64 constant folding in the
+          reference's material graph (e.g. `(1 - metallic) * 0.16 * specular**2` over Const nodes) and
+          libm-vs-numpy pow, far inside the 1e-4 colour budget
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import scenes
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, '*.npz')))
+COLOR_TOL = 2e-6
+
+
+def _lighting(tina, g):
+    L = tina.Lighting()
+    L.nlights[None] = len(g['light_dirs'])
+    L.light_dirs[:len(g['light_dirs'])] = g['light_dirs']
+    L.light_colors[:len(g['light_colors'])] = g['light_colors']
+    L.ambient_color[None] = g['ambient']
+    return L
+
+
+def _material(tina, g, k):
+    ns = {n: getattr(tina, n) for n in ('PBR', 'Classic', 'Diffuse', 'Lamp', 'Lambert', 'Phong', 'Emission', 'CookTorrance', 'Texture')}
+    for i in range(4):
+        if f'tex{i}' in g:
+            ns[f'tex{i}'] = g[f'tex{i}']
+    return eval(str(g[f'material{k}']), ns)
+
+
+def test_goldens_exist():
+    assert len(CASES) >= 9
+
+
+@pytest.mark.parametrize('case', CASES)
+def test_oracle_matches_reference_sources(tina, O, case):
+    g = np.load(os.path.join(GOLDEN, case + '.npz'))
+    W, H = (int(v) for v in g['res'])
+    flags = int(g['flags'])
+    lighting = _lighting(tina, g)
+    depth = O.clear_depth(W, H)
+    image = np.empty((W, H, 3), np.float32)
+    image[...] = g['bgcolor']
+    with np.errstate(all='ignore'):
+        for k in range(int(g['nobjects'])):
+            verts = g[f'verts{k}']
+            norms = g[f'norms{k}'] if f'norms{k}' in g else None
+            coors = g[f'coors{k}'] if f'coors{k}' in g else None
+            occup, depth, tie, _ = O.render_occup(verts, g['W2V'], W, H, flags, g['bias'], depth)
+            assert np.array_equal(occup, g[f'occup{k}']), f'occup of object {k}: {(occup != g[f"occup{k}"]).sum()} px differ'
+            O.render_color(verts, norms, coors, occup, g['W2V'], g['V2W'], W, H, flags, _material(tina, g, k), lighting, image, g['bias'])
+    assert np.array_equal(depth, g['depth'])
+    ok = np.isfinite(g['image_pre_tonemap'])
+    assert np.array_equal(np.isfinite(image), ok)
+    assert np.abs(image[ok] - g['image_pre_tonemap'][ok]).max() <= COLOR_TOL
+    final = O.tonemap(image)
+    ok = np.isfinite(g['image'])
+    assert np.abs(final[ok] - g['image'][ok]).max() <= COLOR_TOL
+    assert (depth < 2**30).sum() > 100
+
+
+def test_mesh_providers_match_reference_set_object(tina, O):
+    """The arrays the reference's set_object kernel wrote into raster.verts / norms / coors
+    (MeshModel, MeshGrid.pre_compute, MeshTransform, MeshNoCulling, MeshFlipCulling, MeshFlipNormal,
+    glTF node transforms) equal the oracle-side providers bit for bit."""
+    # MeshModel
+    g = np.load(os.path.join(GOLDEN, 'monkey_flat_diffuse.npz'))
+    v, vn, vt = O.indexed(scenes.load_monkey())
+    assert np.array_equal(v, g['verts0'])
+    # MeshNoCulling(MeshGrid) with per-frame normals
+    g = np.load(os.path.join(GOLDEN, 'grid_wave_nocull_smooth_classic.npz'))
+    pos = np.load(os.path.join(GOLDEN, 'grid_wave_pos.npy'))
+    p0, _ = O.grid_positions(14, 14)
+    assert np.array_equal(p0[..., :2], pos[..., :2])  # MeshGrid init (grid.py:17-21)
+    fv, fn, _ = O.no_culling(O.grid_faces(pos), O.grid_faces(O.grid_normals(pos)))
+    assert np.array_equal(fv, g['verts0']) and np.array_equal(fn, g['norms0'])
+    # MeshFlipNormal(MeshFlipCulling(MeshTransform(MeshModel)))
+    g = np.load(os.path.join(GOLDEN, 'monkey_transform_flip_lights_addmaterial.npz'))
+    trans = np.load(os.path.join(GOLDEN, 'monkey_trans.npy'))
+    assert np.array_equal(trans, tina.translate([0.2, -0.1, 0.3]) @ tina.eularXYZ([0.3, 0.8, -0.2]) @ tina.scale([0.9, 1.1, 0.8]))
+    v, vn = O.transform(v, vn, trans)
+    assert np.array_equal(v[:, ::-1], g['verts0']) and np.array_equal(-vn[:, ::-1], g['norms0'])
+    assert np.array_equal(vt[:, ::-1], g['coors0'])
+    # glTF: loader + node TRS + MeshTransform(MeshModel)
+    g = np.load(os.path.join(GOLDEN, 'cornell_pbr_textured.npz'))
+    gltf = scenes.load_cornell()
+    objs = scenes.cornell_oracle_objects(gltf)
+    assert len(objs) == int(g['nobjects']) == 3
+    for k, (v, vn, vt, mat) in enumerate(objs):
+        assert np.array_equal(v, g[f'verts{k}']) and np.array_equal(vn, g[f'norms{k}']) and np.array_equal(vt, g[f'coors{k}'])
+    assert np.array_equal(gltf.images[0], g['tex0'])
+    # camera: engine.set_camera (engine.py:72-76) of the same view/proj
+    view, proj = tina.orbit_camera(center=(0, 2, 0), radius=6.0, theta=0.2, phi=0.7)
+    assert np.array_equal((proj @ view).astype(np.float32), g['W2V'])
+    assert np.array_equal(np.linalg.inv(proj @ view).astype(np.float32), g['V2W'])
+
+
+def test_camera_helpers_match_reference(tina):
+    g = np.load(os.path.join(GOLDEN, 'monkey_flat_diffuse.npz'))
+    W2V = tina.perspective(60, 1.0) @ tina.lookat()
+    assert np.array_equal(W2V.astype(np.float32), g['W2V'])
+    g = np.load(os.path.join(GOLDEN, 'grid_wave_nocull_smooth_classic.npz'))
+    W2V = tina.perspective(60, 80 / 60) @ tina.lookat(back=(1.0, 1.5, 2.5))
+    assert np.array_equal(W2V.astype(np.float32), g['W2V'])
+    # default lights (scene/raster.py:90-93)
+    L = tina.Lighting()
+    L.add_light(dir=[1, 2, 3], color=[0.9, 0.9, 0.9])
+    assert np.array_equal(L.light_dirs[0], g['light_dirs'][0]) and np.array_equal(L.light_colors[0], g['light_colors'][0])
