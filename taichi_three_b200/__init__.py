@@ -19,3 +19,4 @@ from .triangle import TriangleRaster
 from .scene import Scene
 from .control import Control, RotationStep
 from .field import Field
+from . import multigpu

@@ -74,6 +74,16 @@ class Engine:
         """engine.py:68-70."""
         _lib.check(_lib.lib().tina_engine_clear_depth(self._h, _stream()))
 
+    def set_face_base(self, base):
+        """Offset of the next render_occup's face ids (sort-last multi-GPU: global ids)."""
+        _lib.check(_lib.lib().tina_engine_set_face_base(self._h, int(base)))
+
+    @property
+    def face_base(self):
+        v = C.c_uint32()
+        _lib.check(_lib.lib().tina_engine_get_face_base(self._h, C.byref(v)))
+        return int(v.value)
+
     def randomize_bias(self, center=False):
         """engine.py:31-39 (TAA jitter)."""
         self.bias[None] = [0.5, 0.5] if center else np.random.rand(2).astype(np.float32)

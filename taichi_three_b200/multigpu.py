@@ -1,0 +1,85 @@
+"""Multi-GPU sharding of the raster path.  One process per GPU (torchrun); the
+reference has no distributed code, so this is host-side orchestration over the same kernels:
+
+  * view-parallel: independent views / frames are dealt round-robin to ranks, no collective;
+  * sort-last: contiguous face ranges per rank, global face ids via Engine.face_base, one elementwise
+    MIN all-reduce of the packed int64 (depth, face-id) keys (NCCL over NVLink on GPUs, gloo in the CPU
+    tests), after which every rank shades exactly the pixels whose winning face it owns.  `min` on the
+    packed key is associative and commutative, so the result is bit-identical to a single GPU.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+CLEAR_KEY = (2**30) << 32  # engine.py:68-70 depth clear, no winner
+
+
+def view_partition(nviews, rank, world):
+    """Indices of the views rank `rank` renders (k = rank mod world)."""
+    return list(range(rank, nviews, world))
+
+
+def face_range(nfaces, rank, world):
+    """Contiguous [lo, hi) face range of `rank`; ranges tile [0, nfaces) in rank order."""
+    base, rem = divmod(nfaces, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def pack_keys(depth, occup, face_base=0):
+    """int32 depth + int32 occup (-1 = none) -> int64 keys, as the kernels store them."""
+    depth = torch.as_tensor(depth).to(torch.int64)
+    ids = torch.as_tensor(occup).to(torch.int64) + 1 + face_base
+    ids = torch.where(torch.as_tensor(occup) < 0, torch.zeros_like(ids), ids)
+    return (depth << 32) | ids
+
+
+def unpack_keys(keys, face_base=0, nfaces=None):
+    """-> (depth int32, occup int32) for faces [face_base, face_base + nfaces)."""
+    keys = torch.as_tensor(keys)
+    depth = (keys >> 32).to(torch.int32)
+    ids = keys & 0xffffffff
+    f = ids - 1 - face_base
+    ok = (ids != 0) & (f >= 0)
+    if nfaces is not None:
+        ok &= f < nfaces
+    return depth, torch.where(ok, f, torch.full_like(f, -1)).to(torch.int32)
+
+
+def composite_min(keys, group=None):
+    """Sort-last merge: in-place elementwise MIN of the packed keys across ranks."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(keys, op=dist.ReduceOp.MIN, group=group)
+    return keys
+
+
+def render_sort_last(engine, raster, verts, norms, coors, shader, bgcolor=0.0, group=None):
+    """One sort-last frame.  `verts/norms/coors` are this rank's CUDA slices of the global face arrays
+    (range = face_range(N, rank, world)); returns the composited [W, H, 3] image on every rank."""
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    counts = torch.tensor([verts.shape[0]], dtype=torch.int64, device=verts.device)
+    allc = [torch.zeros_like(counts) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(allc, counts, group=group)
+    else:
+        allc = [counts]
+    lo = int(sum(int(c.item()) for c in allc[:rank]))
+    engine.clear_depth()
+    engine.set_face_base(lo)
+    raster.set_face_verts(verts)
+    if raster.smoothing:
+        raster.set_face_norms(norms)
+    if raster.texturing:
+        raster.set_face_coors(coors)
+    raster.render_occup()
+    composite_min(engine.keys, group)
+    img = shader.img.to_torch() if hasattr(shader.img, 'to_torch') else shader.img
+    img.zero_()
+    raster.render_color(shader)  # shades pixels whose winner is in [lo, lo + n)
+    if world > 1:
+        dist.all_reduce(img, op=dist.ReduceOp.SUM, group=group)  # exactly one non-zero contributor per pixel
+    empty = (engine.keys & 0xffffffff) == 0
+    bg = torch.as_tensor(np.broadcast_to(np.asarray(bgcolor, dtype=np.float32), (3,)).copy(), device=img.device)
+    img[empty] = bg
+    return img
