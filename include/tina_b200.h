@@ -132,11 +132,15 @@ int tina_raster_set_faces(TinaRaster *r, const float *verts, const float *norms,
                           int64_t nfaces, int borrow, void *stream);
 /* set_object for MeshModel (+MeshTransform, +MeshNoCulling/FlipCulling/FlipNormal):
  * mesh/model.py:56-73, mesh/trans.py:28-40, mesh/cull.py:6-57.
- * faces [N,3,3] int32 = [corner][v, vt, vn].  trans_host / trans_normal_host may be NULL.
+ * v [nverts,3], vt [*,2], vn [nnorms,3]; faces [N,3,3] int32 = [corner][v, vt, vn].
+ * trans_host / trans_normal_host may be NULL.
  * mode bits: 1 = double sided (MeshNoCulling), 2 = flip winding (MeshFlipCulling),
- *            4 = negate normals (MeshFlipNormal). */
-int tina_raster_set_faces_indexed(TinaRaster *r, const float *v, const float *vt, const float *vn,
-                                  const int32_t *faces, int64_t nfaces, const float *trans_host,
+ *            4 = negate normals (MeshFlipNormal).
+ * Indexed sources are NOT expanded: a per-unique-vertex stage (world position / normal here, clip
+ * coordinates in render_occup) feeds the kernels through the mesh's own index buffer, which must
+ * stay valid until the next set_faces*.  tina_raster_materialize writes the expanded copies. */
+int tina_raster_set_faces_indexed(TinaRaster *r, const float *v, int64_t nverts, const float *vt, const float *vn,
+                                  int64_t nnorms, const int32_t *faces, int64_t nfaces, const float *trans_host,
                                   const float *trans_normal_host, uint32_t mode, void *stream);
 /* set_object for MeshGrid (mesh/grid.py:26-58): pos [nx,ny,3]; recomputes the
  * per-vertex normals like MeshGrid.pre_compute, texcoords (i/(nx-1), j/(ny-1)). */
@@ -149,7 +153,10 @@ int tina_raster_render_color(TinaRaster *r, const TinaMaterial *mat_host, const 
                              float *image, uint32_t flags, const float *bg_host, void *stream);
 /* materialise TriangleRaster.occup as int32[W*H] (-1 = none) for the last render_occup */
 int tina_raster_occup(TinaRaster *r, int32_t *occup, void *stream);
-/* device views of the current object's attribute buffers (may be NULL) */
+/* write the expanded [N,3,3] / [N,3,2] copies of the current object (the reference's raster.verts /
+ * norms / coors fields, triangle.py:18-22) if the indexed path skipped them */
+int tina_raster_materialize(TinaRaster *r, void *stream);
+/* device views of the current object's expanded attribute buffers (NULL until materialised) */
 int tina_raster_buffers(TinaRaster *r, const float **verts, const float **norms, const float **coors,
                         int64_t *nfaces);
 /* strategy knobs (every setting yields identical bits); which:
@@ -157,13 +164,16 @@ int tina_raster_buffers(TinaRaster *r, const float **verts, const float **norms,
  * 2 = force every face through the tile path, 3 = collect stats, 4 = record CUDA events around
  * every kernel (tina_raster_kernel_times), 5 = candidate tightening on/off, 6 = read the key
  * before the atomicMin on/off, 7 = largest queue the tile path handles without binning,
- * 8 = always interpret the material program (no specialised shading kernels) */
+ * 8 = always interpret the material program (no specialised shading kernels),
+ * 9 = warp-shared candidate walk in the setup kernel: 0 never, 1 decide per warp, 2 always,
+ * 10 = programmatic dependent launch of k_raster_faces / k_render_color on/off,
+ * 11 = indexed (per-unique-vertex) path for MeshGrid / MeshModel sources on/off */
 int tina_raster_set_tuning(TinaRaster *r, int which, int value);
 /* counters of the last render_occup (synchronises): faces culled, clipped, per-thread,
  * per-warp, queued for the tile path, tile-list entries */
 int tina_raster_stats(TinaRaster *r, int64_t *out6_host);
-/* ms of the last launch of: [0] k_raster_faces, [3] k_large_path, [4] k_render_color
- * ([1], [2] unused; -1 = never recorded); needs tuning knob 4; synchronises on the events */
+/* ms of the last launch of: [0] k_raster_faces, [1] k_vtx_clip (indexed sources only), [3] k_large_path,
+ * [4] k_render_color ([2] unused; -1 = never recorded); needs tuning knob 4; synchronises on the events */
 int tina_raster_kernel_times(TinaRaster *r, float *ms5_host);
 
 /* ---- frame glue (scene/raster.py:176,202-203) -------------------------------- */

@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'csrc', 'libtina_b200.so')
+LIB_PATH = os.environ.get('TINA_B200_LIB') or os.path.join(_HERE, 'csrc', 'libtina_b200.so')  # env: kernel-variant experiments
 
 TINA_SMOOTHING, TINA_TEXTURING, TINA_CULLING, TINA_CLIPPING = 1, 2, 4, 8
 TINA_COLOR_TONEMAP, TINA_COLOR_FILL_BG = 1, 2
@@ -54,7 +54,8 @@ SIGNATURES = {
     'tina_raster_create': (_i, [C.POINTER(_vp), _vp, _i64, _u32]),
     'tina_raster_destroy': (_i, [_vp]),
     'tina_raster_set_faces': (_i, [_vp, _vp, _vp, _vp, _i64, _i, _vp]),
-    'tina_raster_set_faces_indexed': (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _fp, _fp, _u32, _vp]),
+    'tina_raster_set_faces_indexed': (_i, [_vp, _vp, _i64, _vp, _vp, _i64, _vp, _i64, _fp, _fp, _u32, _vp]),
+    'tina_raster_materialize': (_i, [_vp, _vp]),
     'tina_raster_set_faces_grid': (_i, [_vp, _vp, _i, _i, _fp, _fp, _u32, _vp]),
     'tina_raster_render_occup': (_i, [_vp, _vp]),
     'tina_raster_render_color': (_i, [_vp, C.POINTER(TinaMaterial), C.POINTER(TinaLighting), _vp, _u32, _fp, _vp]),

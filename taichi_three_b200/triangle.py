@@ -89,8 +89,9 @@ class TriangleRaster:
                 raise ValueError('texturing=True needs texture coordinates')
             keep = [v, vt, vn, faces]
             ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
-            _lib.check(L.tina_raster_set_faces_indexed(self._h, ptr(v), ptr(vt) if self.texturing else None,
-                                                       ptr(vn) if self.smoothing else None, ptr(faces), n, trans, tn,
+            _lib.check(L.tina_raster_set_faces_indexed(self._h, ptr(v), v.shape[0], ptr(vt) if self.texturing else None,
+                                                       ptr(vn) if self.smoothing else None,
+                                                       vn.shape[0] if vn is not None else 0, ptr(faces), n, trans, tn,
                                                        s.mode, st))
         elif s.kind == 'grid':
             keep = [s.pos]
@@ -168,13 +169,17 @@ class TriangleRaster:
         return Field(self._occup)
 
     def _buffers(self):
+        # the indexed path (MeshGrid / MeshModel) keeps no expanded copies until somebody reads them
+        _lib.check(_lib.lib().tina_raster_materialize(self._h, _stream()))
         v, n, t, nf = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_int64()
         _lib.check(_lib.lib().tina_raster_buffers(self._h, C.byref(v), C.byref(n), C.byref(t), C.byref(nf)))
         return v.value, n.value, t.value, nf.value
 
     @property
     def nfaces(self):
-        return self._buffers()[3]
+        nf = C.c_int64()
+        _lib.check(_lib.lib().tina_raster_buffers(self._h, None, None, None, C.byref(nf)))
+        return nf.value
 
     @property
     def verts(self):
@@ -195,16 +200,18 @@ class TriangleRaster:
         """ms of the last launch of each kernel (needs set_tuning(profile=1)); -1 = not recorded."""
         out = (C.c_float * 5)()
         _lib.check(_lib.lib().tina_raster_kernel_times(self._h, out))
-        return dict(zip(('raster_faces', 'unused1', 'unused2', 'large_path', 'render_color'), list(out)))
+        return dict(zip(('raster_faces', 'vtx_clip', 'unused2', 'large_path', 'render_color'), list(out)))
 
     def set_tuning(self, tiny_max=None, force_tiles=None, collect_stats=None, profile=None, tighten=None,
-                   precheck=None, scan_max=None, generic_vm=None):
+                   precheck=None, scan_max=None, generic_vm=None, balance=None, pdl=None, indexed=None):
         """Strategy knobs (every setting produces identical bits): tiny_max = most candidate pixels a
         face may have to be rasterised per thread in the setup kernel (more -> tile path);
         force_tiles = every face through the tile path; tighten = skip bbox pixels whose sample
         provably fails (0 = walk the full reference bbox); precheck = read the key before the
         atomicMin; scan_max = largest queue the tile path handles without binning;
-        generic_vm = always interpret the material program."""
+        generic_vm = always interpret the material program; balance = warp-shared candidate walk in
+        the setup kernel (0 never, 1 auto per warp, 2 always); pdl = programmatic dependent launch;
+        indexed = per-unique-vertex stage for MeshGrid / MeshModel (takes effect at the next set_object)."""
         L = _lib.lib()
         if tiny_max is not None:
             _lib.check(L.tina_raster_set_tuning(self._h, 0, int(tiny_max)))
@@ -214,7 +221,7 @@ class TriangleRaster:
             _lib.check(L.tina_raster_set_tuning(self._h, 3, int(collect_stats)))
         if profile is not None:
             _lib.check(L.tina_raster_set_tuning(self._h, 4, int(profile)))
-        for which, v in ((5, tighten), (6, precheck), (7, scan_max), (8, generic_vm)):
+        for which, v in ((5, tighten), (6, precheck), (7, scan_max), (8, generic_vm), (9, balance), (10, pdl), (11, indexed)):
             if v is not None:
                 _lib.check(L.tina_raster_set_tuning(self._h, which, int(v)))
 

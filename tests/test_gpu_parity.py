@@ -101,7 +101,9 @@ def _render_soup(tina, tri, W, H, view, proj, **tuning):
     return scene
 
 
-@pytest.mark.parametrize('tuning', [dict(), dict(tiny_max=0), dict(tiny_max=4), dict(tiny_max=100000), dict(force_tiles=1)])
+@pytest.mark.parametrize('tuning', [dict(), dict(tiny_max=0), dict(tiny_max=4), dict(tiny_max=100000), dict(force_tiles=1),
+                                    dict(balance=0), dict(balance=2), dict(balance=2, tiny_max=2000), dict(balance=0, tiny_max=2000),
+                                    dict(precheck=1, balance=2)])
 def test_soup_depth_complexity_all_strategies(tina, O, tuning):
     """C3-style at test size: random soup with depth complexity ~8; every rasteriser strategy
     (per-thread direct / binned tile path / mixtures) must give the same bits."""
@@ -344,7 +346,7 @@ def test_tightening_is_exact(tina, O, seed, bias):
             scene.add_object(mesh)
             scene.engine.set_camera(view, proj)
             scene.engine.bias[None] = bias
-            scene.triangle_raster.set_tuning(tighten=tighten, tiny_max=64)
+            scene.triangle_raster.set_tuning(tighten=tighten, tiny_max=64, balance=2 if tighten else 0)
             scene.render()
             out.append(_keys(scene))
         assert np.array_equal(out[-1], out[-2]), f'tightening changed {(out[-1] != out[-2]).sum()} keys (culling={culling})'
@@ -445,3 +447,47 @@ def test_cuda_path_matches_reference_goldens(tina, path):
     ok = np.isfinite(g['image_pre_tonemap'])
     assert np.array_equal(np.isfinite(out), ok)
     assert np.abs(out[ok] - g['image_pre_tonemap'][ok]).max() <= COLOR_TOL
+
+
+@pytest.mark.parametrize('case', ['grid', 'grid_nonsquare', 'grid_nocull_trans', 'model', 'model_trans_flip', 'model_nocull_big'])
+def test_indexed_vertex_stage_equals_expanded_path(tina, O, case):
+    """MeshGrid / MeshModel sources go through the per-unique-vertex stage (world + clip coordinates per
+    vertex, corners fetched through the mesh's own indexing); it must give exactly the bits of the
+    expanded-array path (the reference's raster.verts/norms/coors), for keys and colours."""
+    import torch
+    W, H = 320, 240
+    view, proj = tina.orbit_camera(radius=3.0, theta=0.35, phi=0.6, aspect=W / H)
+    trans = tina.translate([0.1, -0.2, 0.1]) @ tina.eularXYZ([0.4, -0.3, 0.2]) @ tina.scale([1.3, 0.8, 1.1])
+
+    def build():
+        if case.startswith('grid'):
+            g = tina.MeshGrid((40, 56) if case == 'grid_nonsquare' else 48)
+            pos = g.pos.to_numpy()
+            pos[..., 2] = 0.15 * np.sin(7 * pos[..., 0]) * np.cos(5 * pos[..., 1])
+            g.pos.from_numpy(pos)
+            m = g
+            if case == 'grid_nocull_trans':
+                m = tina.MeshNoCulling(tina.MeshTransform(g, trans))
+        else:
+            m = tina.MeshModel(scenes.load_monkey())
+            if case == 'model_trans_flip':
+                m = tina.MeshFlipNormal(tina.MeshFlipCulling(tina.MeshTransform(m, trans)))
+            if case == 'model_nocull_big':
+                m = tina.MeshNoCulling(tina.MeshTransform(m, tina.scale(2.5)))  # big triangles -> tile path too
+        return m
+
+    res = []
+    for indexed in (1, 0):
+        scene = tina.Scene((W, H), smoothing=True, texturing=True, tonemap=False)
+        img = np.random.default_rng(0).random((8, 8, 3)).astype(np.float32)
+        mat = tina.PBR(basecolor=tina.Texture(img), metallic=0.3, roughness=0.4) if 'trans' in case else tina.Classic()
+        scene.add_object(build(), mat)
+        scene.engine.set_camera(view, proj)
+        scene.triangle_raster.set_tuning(indexed=indexed)
+        scene.render()
+        torch.cuda.synchronize()
+        res.append((_keys(scene), scene.img.to_numpy(), scene.triangle_raster.verts.to_numpy(),
+                    scene.triangle_raster.norms.to_numpy(), scene.triangle_raster.coors.to_numpy()))
+    for a, b in zip(res[0], res[1]):
+        assert np.array_equal(a, b)
+    assert ((res[0][0] & 0xffffffff) != 0).sum() > 2000
