@@ -83,7 +83,10 @@ enum {
     TINA_OP_MIX = 7,     /* pop b, a, fac; push (1-fac)*a + fac*b                      material.py:96-118 */
     TINA_OP_MUL = 8,     /* pop wei, fac; push fac*wei                                 material.py:157-176 */
     TINA_OP_ADD = 9,     /* pop b, a; push a+b                                         material.py:204-220 */
+    TINA_OP_REG = 10,    /* push register[arg] (written by the per-pixel prologue program)               */
+    TINA_OP_STORE = 11,  /* pop -> register[arg]                                                         */
 };
+#define TINA_MAX_REGS 8
 
 typedef struct {
     int32_t op;
@@ -97,6 +100,10 @@ typedef struct {
     int32_t n_brdf, n_ambient, n_emission, ntex;
     const float *tex[TINA_MAX_TEX]; /* device, [w][h][c] f32, x-major (advans.py:8-28) */
     int32_t tex_w[TINA_MAX_TEX], tex_h[TINA_MAX_TEX], tex_c[TINA_MAX_TEX];
+    /* optional 4th program after emission: run ONCE per pixel before lighting; it evaluates the
+     * light-independent, non-constant sub-expressions the host hoisted out of the other three
+     * (texture samples, Fresnel factors, ...) into registers they then read with TINA_OP_REG */
+    int32_t n_prologue, pad_[3];
     TinaInstr code[TINA_MAX_INSTR];
 } TinaMaterial;
 
@@ -151,6 +158,23 @@ int tina_raster_render_occup(TinaRaster *r, void *stream);
 /* triangle.py:134-153 + shader.py:119-131 + lighting.py:84-98; image [W,H,3] f32 */
 int tina_raster_render_color(TinaRaster *r, const TinaMaterial *mat_host, const TinaLighting *light_host,
                              float *image, uint32_t flags, const float *bg_host, void *stream);
+/* G-buffer sinks of core/shader.py:21-109 for the current object (ShaderGroup fan-out, shader.py:138-148):
+ * writes `ncomp` (1..3) float32 (or int32 if out_is_int) values per pixel where the object is visible,
+ * out[(x*H + y)*ncomp + k].  param_host: ConstShader value (3 floats) / ChessboardShader size (1 float). */
+enum {
+    TINA_SINK_CONST = 0,      /* shader.py:21-28  */
+    TINA_SINK_POSITION = 1,   /* shader.py:31-34  */
+    TINA_SINK_DEPTH = 2,      /* shader.py:37-40  */
+    TINA_SINK_NORMAL = 3,     /* shader.py:43-46  */
+    TINA_SINK_VIEWNORMAL = 4, /* shader.py:49-56  */
+    TINA_SINK_TEXCOORD = 5,   /* shader.py:59-62  */
+    TINA_SINK_COLOR = 6,      /* shader.py:65-68  */
+    TINA_SINK_CHESSBOARD = 7, /* shader.py:71-79  */
+    TINA_SINK_VIEWDIR = 8,    /* shader.py:96-101 */
+    TINA_SINK_SIMPLE = 9,     /* shader.py:104-109 */
+};
+int tina_raster_render_gbuffer(TinaRaster *r, int kind, void *out, int ncomp, int out_is_int, const float *param_host,
+                               void *stream);
 /* materialise TriangleRaster.occup as int32[W*H] (-1 = none) for the last render_occup */
 int tina_raster_occup(TinaRaster *r, int32_t *occup, void *stream);
 /* write the expanded [N,3,3] / [N,3,2] copies of the current object (the reference's raster.verts /
@@ -167,7 +191,9 @@ int tina_raster_buffers(TinaRaster *r, const float **verts, const float **norms,
  * 8 = always interpret the material program (no specialised shading kernels),
  * 9 = warp-shared candidate walk in the setup kernel: 0 never, 1 decide per warp, 2 always,
  * 10 = programmatic dependent launch of k_raster_faces / k_render_color on/off,
- * 11 = indexed (per-unique-vertex) path for MeshGrid / MeshModel sources on/off */
+ * 11 = indexed (per-unique-vertex) path for MeshGrid / MeshModel sources on/off,
+ * 12 = adaptive tile path: after 8 consecutive render_occup/render_color pairs that queued no large
+ *      face the tile-path kernel is not launched and the setup kernel walks large faces itself */
 int tina_raster_set_tuning(TinaRaster *r, int which, int value);
 /* counters of the last render_occup (synchronises): faces culled, clipped, per-thread,
  * per-warp, queued for the tile path, tile-list entries */

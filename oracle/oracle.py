@@ -18,8 +18,8 @@ _lib = None
 
 
 def build(force=False):
-    src = os.path.join(_HERE, 'tina_oracle.c')
-    if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, 'tina_oracle.c'), os.path.join(os.path.dirname(_HERE), 'include', 'tina_b200.h')]
+    if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < max(os.path.getmtime(p) for p in srcs):
         subprocess.run(['make', '-C', _HERE, 'libtina_oracle.so'], check=True, capture_output=True)
     return LIB_PATH
 
@@ -84,6 +84,7 @@ def render_color(verts, norms, coors, occup, W2V, V2W, W, H, flags, material, li
     brdf, amb, emi, textures = flatten_material(material)
     m = P.TinaMaterial()
     m.n_brdf, m.n_ambient, m.n_emission, m.ntex = len(brdf), len(amb), len(emi), len(textures)
+    m.n_prologue = 0  # the oracle interprets the plain, unfolded, unhoisted programs
     for i, (op, arg, c) in enumerate(brdf + amb + emi):
         m.code[i].op, m.code[i].arg = op, arg
         m.code[i].c[0], m.code[i].c[1], m.code[i].c[2] = c
@@ -102,6 +103,20 @@ def render_color(verts, norms, coors, occup, W2V, V2W, W, H, flags, material, li
                            _p(_f(bias)), W, H, C.c_uint32(flags), C.byref(m), texptrs, C.byref(L), _p(image),
                            1 if parallel else 0)
     return image
+
+
+def render_gbuffer(kind, verts, norms, coors, occup, depth, W2V, V2W, W, H, flags, out, param=(0, 0, 0), bias=(0.5, 0.5)):
+    """core/shader.py:21-109 sinks; `out` [W,H,n] f32 is modified in place where occup != -1."""
+    verts = _f(verts).reshape(-1, 9)
+    norms = _f(norms).reshape(-1, 9) if norms is not None else None
+    coors = _f(coors).reshape(-1, 6) if coors is not None else None
+    assert out.dtype == np.float32 and out.flags['C_CONTIGUOUS']
+    ncomp = out.size // (W * H)
+    lib().orc_render_gbuffer(_p(verts), _p(norms), _p(coors), _p(np.ascontiguousarray(occup, dtype=np.int32)),
+                             _p(np.ascontiguousarray(depth, dtype=np.int32)), _p(_f(W2V).reshape(16)), _p(_f(V2W).reshape(16)),
+                             _p(_f(bias)), W, H, C.c_uint32(flags), int(kind), _p(_f(np.resize(np.asarray(param, np.float32), 3))),
+                             _p(out), ncomp)
+    return out
 
 
 def tonemap(image):

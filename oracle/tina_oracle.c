@@ -446,6 +446,74 @@ void orc_render_color(const float *verts, const float *norms, const float *coors
         }
 }
 
+/*
+ * core/shader.py:21-109 G-buffer sinks for pixels with occup != -1: out[(x*H+y)*ncomp + k].
+ * kind: 0 Const(param) 1 Position 2 Depth 3 Normal 4 ViewNormal 5 Texcoord 6 Color 7 Chessboard(param[0])
+ *       8 Viewdir 9 Simple
+ */
+void orc_render_gbuffer(const float *verts, const float *norms, const float *coors, const int32_t *occup,
+                        const int32_t *depth, const float *W2V, const float *V2W, const float *bias, int W, int H,
+                        uint32_t flags, int kind, const float *param, float *out, int ncomp) {
+    for (int x = 0; x < W; x++)
+        for (int y = 0; y < H; y++) {
+            int64_t P = (int64_t)x * H + y;
+            int32_t f = occup[P];
+            if (f == -1) continue;
+            const float *V9 = verts + (int64_t)f * 9;
+            FaceSetup s;
+            face_setup(V9, W2V, W, H, 0u, &s);
+            float wei[3];
+            pixel_weights(&s, x, y, bias, wei);
+            const float *A = V9, *B = V9 + 3, *C = V9 + 6;
+            float pos[3], nrm[3], uv[2] = {0, 0}, v[3] = {0, 0, 0};
+            for (int k = 0; k < 3; k++) pos[k] = (wei[0] * A[k] + wei[1] * B[k]) + wei[2] * C[k];
+            if (flags & TINA_SMOOTHING) {
+                const float *N9 = norms + (int64_t)f * 9;
+                for (int k = 0; k < 3; k++) nrm[k] = (wei[0] * N9[k] + wei[1] * N9[3 + k]) + wei[2] * N9[6 + k];
+            } else {
+                float e1[3] = {B[0] - A[0], B[1] - A[1], B[2] - A[2]}, e2[3] = {C[0] - A[0], C[1] - A[1], C[2] - A[2]};
+                cross3(e1, e2, nrm);
+            }
+            normalize3(nrm);
+            if (flags & TINA_TEXTURING) {
+                const float *T6 = coors + (int64_t)f * 6;
+                for (int k = 0; k < 2; k++) uv[k] = (wei[0] * T6[k] + wei[1] * T6[2 + k]) + wei[2] * T6[4 + k];
+            }
+            float p[2] = {(float)x + bias[0], (float)y + bias[1]};
+            float q[3] = {p[0] / (float)W * 2.0f - 1.0f, p[1] / (float)H * 2.0f - 1.0f, -1.0f}, ro[3], ro1[3], vd[3];
+            mapply_pos(V2W, q, ro);
+            q[2] = 1.0f;
+            mapply_pos(V2W, q, ro1);
+            for (int k = 0; k < 3; k++) vd[k] = ro1[k] - ro[k];
+            normalize3(vd);
+            for (int k = 0; k < 3; k++) vd[k] = -vd[k];
+            switch (kind) {
+            case 0: v[0] = param[0], v[1] = param[1], v[2] = param[2]; break;
+            case 1: memcpy(v, pos, sizeof v); break;
+            case 2: v[0] = v[1] = v[2] = (float)depth[P]; break;
+            case 3: memcpy(v, nrm, sizeof v); break;
+            case 4: { /* shader.py:51-58 mapply_dir(W2V, normal).normalized() */
+                float r[3], rw;
+                mapply(W2V, nrm, 0.0f, r, &rw);
+                normalize3(r);
+                memcpy(v, r, sizeof v);
+                break;
+            }
+            case 5: v[0] = uv[0], v[1] = uv[1]; break;
+            case 6: v[0] = v[1] = v[2] = 1.0f; break;
+            case 7: { /* shader.py:73-79 */
+                float fac = fmodf(floorf(p[0] / param[0]) + floorf(p[1] / param[0]), 2.0f);
+                if (fac < 0) fac += 2.0f;
+                v[0] = v[1] = v[2] = 0.4f * (1.0f - fac) + 0.9f * fac;
+                break;
+            }
+            case 8: for (int k = 0; k < 3; k++) v[k] = vd[k] * 0.5f + 0.5f; break;
+            default: v[0] = v[1] = v[2] = fabsf(dot3(nrm, vd)); break;
+            }
+            for (int k = 0; k < ncomp; k++) out[P * ncomp + k] = v[k];
+        }
+}
+
 /* ---- mesh providers feeding set_object ------------------------------------------ */
 
 /* mesh/grid.py:26-35 MeshGrid.pre_compute; pos, nrm: [nx][ny][3] */

@@ -11,7 +11,8 @@ from .material import (Node, Const, Param, Input, Texture, FresnelFactor, IMater
                        flatten_material)
 from .assimp import readobj, readgltf, objverts, objnorms, objcoors, objorient, objautoscale
 from .lighting import Lighting
-from .shader import IShader, Shader, ShaderGroup
+from .shader import (IShader, Shader, ShaderGroup, ConstShader, PositionShader, DepthShader, NormalShader,
+                     ViewNormalShader, TexcoordShader, ColorShader, ChessboardShader, ViewdirShader, SimpleShader)
 from .mesh import (MAX, SimpleMesh, MeshModel, MeshGrid, MeshTransform, MeshFlipCulling, MeshNoCulling,
                    MeshFlipNormal, MeshFlatNormal, MeshSmoothNormal, MeshEditBase)
 from .engine import Engine

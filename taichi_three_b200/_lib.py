@@ -13,7 +13,10 @@ TINA_COLOR_TONEMAP, TINA_COLOR_FILL_BG = 1, 2
 TINA_MAX_LIGHTS, TINA_MAX_INSTR, TINA_MAX_TEX = 16, 96, 4
 
 (OP_CONST, OP_INPUT, OP_TEXTURE, OP_FRESNEL, OP_LAMBERT, OP_PHONG, OP_COOK, OP_MIX, OP_MUL,
- OP_ADD) = range(10)
+ OP_ADD, OP_REG, OP_STORE) = range(12)
+TINA_MAX_REGS = 8
+(SINK_CONST, SINK_POSITION, SINK_DEPTH, SINK_NORMAL, SINK_VIEWNORMAL, SINK_TEXCOORD, SINK_COLOR, SINK_CHESSBOARD,
+ SINK_VIEWDIR, SINK_SIMPLE) = range(10)
 
 
 class TinaLighting(C.Structure):
@@ -33,6 +36,7 @@ class TinaMaterial(C.Structure):
                 ('tex', C.c_void_p * TINA_MAX_TEX),
                 ('tex_w', C.c_int32 * TINA_MAX_TEX), ('tex_h', C.c_int32 * TINA_MAX_TEX),
                 ('tex_c', C.c_int32 * TINA_MAX_TEX),
+                ('n_prologue', C.c_int32), ('pad_', C.c_int32 * 3),
                 ('code', TinaInstr * TINA_MAX_INSTR)]
 
 
@@ -59,6 +63,7 @@ SIGNATURES = {
     'tina_raster_set_faces_grid': (_i, [_vp, _vp, _i, _i, _fp, _fp, _u32, _vp]),
     'tina_raster_render_occup': (_i, [_vp, _vp]),
     'tina_raster_render_color': (_i, [_vp, C.POINTER(TinaMaterial), C.POINTER(TinaLighting), _vp, _u32, _fp, _vp]),
+    'tina_raster_render_gbuffer': (_i, [_vp, _i, _vp, _i, _i, _fp, _vp]),
     'tina_raster_occup': (_i, [_vp, _vp, _vp]),
     'tina_raster_buffers': (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i64)]),
     'tina_raster_set_tuning': (_i, [_vp, _i, _i]),

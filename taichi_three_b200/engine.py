@@ -12,7 +12,13 @@ from . import _lib
 from .field import Field, HostField, wrap_device
 
 
-def _stream():
+_raw_stream = getattr(torch._C, '_cuda_getCurrentRawStream', None)
+
+
+def _stream(device_index=None):
+    """torch's current CUDA stream as a void* (the fast private getter when torch has it)."""
+    if _raw_stream is not None:
+        return C.c_void_p(_raw_stream(torch.cuda.current_device() if device_index is None else device_index))
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
@@ -30,6 +36,7 @@ class Engine:
         h = C.c_void_p()
         _lib.check(L.tina_engine_create(C.byref(h), self.device.index, self.res[0], self.res[1]))
         self._h = h
+        self._clear = L.tina_engine_clear_depth
         kp = C.c_void_p()
         _lib.check(L.tina_engine_keys(self._h, C.byref(kp)))
         #: int64[W, H]  key = depth << 32 | (global face id + 1)
@@ -72,7 +79,9 @@ class Engine:
 
     def clear_depth(self):
         """engine.py:68-70."""
-        _lib.check(_lib.lib().tina_engine_clear_depth(self._h, _stream()))
+        rc = self._clear(self._h, _stream(self.device.index))
+        if rc:
+            _lib.check(rc)
 
     def set_face_base(self, base):
         """Offset of the next render_occup's face ids (sort-last multi-GPU: global ids)."""

@@ -46,6 +46,16 @@ class Lighting:
     def set_ambient_light(self, color):  # lighting.py:68-69
         self.ambient_color[None] = np.array(color, dtype=np.float32)
 
+    def struct_ref(self):
+        """ctypes reference to the current TinaLighting POD (what the C ABI takes)."""
+        L = self.struct()
+        ref = self.__dict__.get('_cache_ref')
+        if ref is None or ref[0] is not L:
+            import ctypes
+            ref = (L, ctypes.byref(L))
+            self._cache_ref = ref
+        return ref[1]
+
     def struct(self):
         """TinaLighting POD, rebuilt only when the light state changed."""
         key = (self.light_dirs.tobytes(), self.light_colors.tobytes(), self.ambient_color.to_numpy().tobytes(),

@@ -368,6 +368,81 @@ def fold_program(code):
     return code_of(stack[0])
 
 
+# ---- hoisting: light-independent sub-expressions are evaluated once per pixel -------------------
+_ARITY = {}
+
+
+def _arity(op):
+    return {_lib.OP_CONST: 0, _lib.OP_INPUT: 0, _lib.OP_LAMBERT: 0, _lib.OP_TEXTURE: 1, _lib.OP_PHONG: 1,
+            _lib.OP_COOK: 2, _lib.OP_FRESNEL: 3, _lib.OP_MIX: 3, _lib.OP_MUL: 2, _lib.OP_ADD: 2, _lib.OP_REG: 0}[op]
+
+
+def _to_tree(code):
+    """postfix -> nested tuples (op, arg, c, children...) with children in push order"""
+    st = []
+    for op, arg, c in code:
+        n = _arity(op)
+        kids = tuple(st[len(st) - n:]) if n else ()
+        del st[len(st) - n:]
+        st.append((op, arg, tuple(c)) + kids)
+    assert len(st) == 1
+    return st[0]
+
+
+def _to_code(tree, out):
+    for kid in tree[3:]:
+        _to_code(kid, out)
+    out.append((tree[0], tree[1], tree[2]))
+    return out
+
+
+def _light_dependent(tree):
+    return tree[0] in (_lib.OP_PHONG, _lib.OP_COOK) or any(_light_dependent(k) for k in tree[3:])
+
+
+def hoist_programs(brdf, amb, emi):
+    """(folded postfix programs) -> (brdf, ambient, emission, prologue).
+    Every maximal light-independent, non-constant sub-expression -- and every texture sample inside one
+    -- is given a register (identical sub-expressions share it), computed by the prologue program once
+    per pixel, and replaced by OP_REG in the three programs.  Same ops on the same values => same bits;
+    what changes is that a texture feeding both the diffuse colour and the Fresnel factor of tina.PBR is
+    sampled once instead of once per use and per light, and that stock materials with textured / per-pixel
+    parameters keep the [X, X, ..., COOK|PHONG, MIX] shapes the specialised shading kernels recognise."""
+    regs = {}      # structural key -> register index
+    prologue = []  # postfix code
+
+    def reg_of(tree):
+        """emit `tree` (light independent, not constant) into the prologue; -> OP_REG leaf"""
+        # inner texture samples get registers of their own so that they are shared
+        kids = tuple(hoist_li(k) for k in tree[3:])
+        tree = tree[:3] + kids
+        if tree in regs:
+            return (_lib.OP_REG, regs[tree], (0.0, 0.0, 0.0))
+        if len(regs) >= _lib.TINA_MAX_REGS:
+            return tree  # out of registers: leave it inline
+        r = len(regs)
+        regs[tree] = r
+        _to_code(tree, prologue)
+        prologue.append((_lib.OP_STORE, r, (0.0, 0.0, 0.0)))
+        return (_lib.OP_REG, r, (0.0, 0.0, 0.0))
+
+    def hoist_li(tree):
+        """inside a light-independent expression: only texture samples are worth a register"""
+        if tree[0] == _lib.OP_TEXTURE:
+            return reg_of(tree)
+        return tree[:3] + tuple(hoist_li(k) for k in tree[3:])
+
+    def hoist(tree):
+        if tree[0] in (_lib.OP_CONST, _lib.OP_REG):
+            return tree
+        if not _light_dependent(tree):
+            return reg_of(tree)
+        return tree[:3] + tuple(hoist(k) for k in tree[3:])
+
+    out = [_to_code(hoist(_to_tree(code)), []) for code in (brdf, amb, emi)]
+    return out[0], out[1], out[2], prologue
+
+
 def _walk(node, seen):
     if id(node) in seen or not isinstance(node, Node):
         return
@@ -390,20 +465,31 @@ def param_signature(material):
     return tuple(p._value.tobytes() for p in params)
 
 
-def material_struct(material, device, fold=True):
-    """Build the TinaMaterial POD; returns (struct, keepalive list of device tensors)."""
+def compile_material(material, fold=True):
+    """flatten -> constant-fold -> hoist.  -> (brdf, ambient, emission, prologue, textures)"""
     brdf, amb, emi, textures = flatten_material(material)
+    pro = []
     if fold:
         brdf, amb, emi = fold_program(brdf), fold_program(amb), fold_program(emi)
+        brdf, amb, emi, pro = hoist_programs(brdf, amb, emi)
+    if len(brdf) + len(amb) + len(emi) + len(pro) > _lib.TINA_MAX_INSTR:
+        raise NotImplementedError('material program too long')
+    return brdf, amb, emi, pro, textures
+
+
+def material_struct(material, device, fold=True):
+    """Build the TinaMaterial POD; returns (struct, keepalive list of device tensors)."""
+    brdf, amb, emi, pro, textures = compile_material(material, fold)
     m = _lib.TinaMaterial()
     m.n_brdf, m.n_ambient, m.n_emission, m.ntex = len(brdf), len(amb), len(emi), len(textures)
+    m.n_prologue = len(pro)
     keep = []
     for i, t in enumerate(textures):
         d = t.device_tensor(device)
         keep.append(d)
         m.tex[i] = d.data_ptr()
         m.tex_w[i], m.tex_h[i], m.tex_c[i] = d.shape[0], d.shape[1], d.shape[2]
-    for i, (op, arg, c) in enumerate(brdf + amb + emi):
+    for i, (op, arg, c) in enumerate(brdf + amb + emi + pro):
         m.code[i].op, m.code[i].arg = op, arg
         m.code[i].c[0], m.code[i].c[1], m.code[i].c[2] = c
     return m, keep

@@ -10,7 +10,7 @@ from .engine import _stream
 from .field import Field, wrap_device
 from .material import material_struct
 from .mesh import MAX, FaceSource, _to_device_f32
-from .shader import Shader, ShaderGroup
+from .shader import Shader, ShaderGroup, _Sink
 
 
 def _fp(a):
@@ -33,6 +33,10 @@ class TriangleRaster:
         h = C.c_void_p()
         _lib.check(L.tina_raster_create(C.byref(h), engine._h, int(maxfaces), self.flags))
         self._h = h
+        self._occup_fn, self._color_fn = L.tina_raster_render_occup, L.tina_raster_render_color
+        self._dev_index = engine.device.index
+        self._shader_cache = {}
+        self._bg_cache = (None, None)
         self._keep = []  # tensors the C side currently aliases
         self._occup = None
         self._occup_stale = True
@@ -123,37 +127,70 @@ class TriangleRaster:
 
     # ---- render_occup (triangle.py:89-131) ---------------------------------------------
     def render_occup(self):
-        _lib.check(_lib.lib().tina_raster_render_occup(self._h, _stream()))
+        rc = self._occup_fn(self._h, _stream(self._dev_index))
+        if rc:
+            _lib.check(rc)
         self._occup_stale = True
 
     # ---- render_color (triangle.py:134-153) --------------------------------------------
     def render_color(self, shader, fill_bg=None, tonemap=False):
         """`shader`: a Shader or a ShaderGroup of Shaders.  fill_bg / tonemap are fusion hints used by Scene.render."""
-        shaders = shader.shaders if isinstance(shader, ShaderGroup) else [shader]
+        shaders = shader.shaders if isinstance(shader, ShaderGroup) else (shader,)
+        flags = (_lib.TINA_COLOR_TONEMAP if tonemap else 0) | (_lib.TINA_COLOR_FILL_BG if fill_bg is not None else 0)
+        bg = None
+        if fill_bg is not None:
+            key, bg = self._bg_cache
+            if key is not fill_bg:  # (callers reuse one array per frame loop)
+                arr = np.ascontiguousarray(np.broadcast_to(np.asarray(fill_bg, dtype=np.float32), (3,)))
+                bg = (arr, arr.ctypes.data_as(C.POINTER(C.c_float)))
+                self._bg_cache = (fill_bg, bg)
+            bg = bg[1]
+        st = _stream(self._dev_index)
         for s in shaders:
-            if not isinstance(s, Shader):
-                raise NotImplementedError(f'{type(s).__name__} is not supported by the B200 render_color yet')
-            img = s.img.to_torch() if hasattr(s.img, 'to_torch') else s.img
-            if img.dtype != torch.float32 or not img.is_contiguous() or img.numel() != self.res[0] * self.res[1] * 3:
-                raise ValueError('shader image must be a contiguous float32 [W, H, 3] CUDA tensor')
+            rec = self._shader_cache.get(id(s))
+            img = s.img
+            if isinstance(s, _Sink):
+                self._render_sink(s, st)
+                continue
+            if rec is None or rec[0] is not s or rec[1] is not img:
+                if not isinstance(s, Shader):
+                    raise NotImplementedError(f'{type(s).__name__} is not supported by the B200 render_color yet')
+                t = img.to_torch() if hasattr(img, 'to_torch') else img
+                if t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != self.res[0] * self.res[1] * 3 or not t.is_cuda:
+                    raise ValueError('shader image must be a contiguous float32 [W, H, 3] CUDA tensor')
+                rec = (s, img, t, C.c_void_p(t.data_ptr()))
+                self._shader_cache[id(s)] = rec
             mat, keep = self._material_struct(s.material)
-            light = s.lighting.struct()
-            flags = (_lib.TINA_COLOR_TONEMAP if tonemap else 0) | (_lib.TINA_COLOR_FILL_BG if fill_bg is not None else 0)
-            bg = _fp(np.broadcast_to(np.asarray(fill_bg if fill_bg is not None else 0, dtype=np.float32), (3,)))
-            _lib.check(_lib.lib().tina_raster_render_color(self._h, C.byref(mat), C.byref(light), C.c_void_p(img.data_ptr()),
-                                                           flags, bg, _stream()))
+            rc = self._color_fn(self._h, mat, s.lighting.struct_ref(), rec[3], flags, bg, st)
+            if rc:
+                _lib.check(rc)
             self._mat_keep = keep
+
+    def _render_sink(self, s, st):
+        """G-buffer shaders (shader.py:21-109) for the current object."""
+        t = s.img.to_torch() if hasattr(s.img, 'to_torch') else s.img
+        npix = self.res[0] * self.res[1]
+        if t.dtype not in (torch.float32, torch.int32) or not t.is_contiguous() or not t.is_cuda or t.numel() % npix:
+            raise ValueError('G-buffer image must be a contiguous float32 / int32 CUDA tensor [W, H] or [W, H, n]')
+        ncomp = t.numel() // npix
+        if not 1 <= ncomp <= 3:
+            raise ValueError('G-buffer image must have 1..3 components')
+        p = s.param()
+        _lib.check(_lib.lib().tina_raster_render_gbuffer(self._h, s.kind, C.c_void_p(t.data_ptr()), ncomp,
+                                                         1 if t.dtype == torch.int32 else 0, _fp(p) if p is not None else None, st))
 
     def _material_struct(self, material):
         """Flattening + folding is pure host work: cache it per material object, keyed by the
         current values of its runtime Param nodes (matr/nodes.py:52-76)."""
         from .material import param_signature
         cache = self.__dict__.setdefault('_mat_cache', {})
-        sig = param_signature(material)
         hit = cache.get(id(material))
+        if hit is not None and hit[3] is material and not hit[4]:
+            return hit[1], hit[2]  # no runtime Param in the graph: nothing can have changed
+        sig = param_signature(material)
         if hit is None or hit[0] != sig or hit[3] is not material:
             mat, keep = material_struct(material, self.engine.device)
-            hit = (sig, mat, keep, material)
+            hit = (sig, C.byref(mat), (keep, mat), material, len(sig) > 0)
             cache[id(material)] = hit
         return hit[1], hit[2]
 
@@ -203,7 +240,7 @@ class TriangleRaster:
         return dict(zip(('raster_faces', 'vtx_clip', 'unused2', 'large_path', 'render_color'), list(out)))
 
     def set_tuning(self, tiny_max=None, force_tiles=None, collect_stats=None, profile=None, tighten=None,
-                   precheck=None, scan_max=None, generic_vm=None, balance=None, pdl=None, indexed=None):
+                   precheck=None, scan_max=None, generic_vm=None, balance=None, pdl=None, indexed=None, adaptive=None):
         """Strategy knobs (every setting produces identical bits): tiny_max = most candidate pixels a
         face may have to be rasterised per thread in the setup kernel (more -> tile path);
         force_tiles = every face through the tile path; tighten = skip bbox pixels whose sample
@@ -211,7 +248,8 @@ class TriangleRaster:
         atomicMin; scan_max = largest queue the tile path handles without binning;
         generic_vm = always interpret the material program; balance = warp-shared candidate walk in
         the setup kernel (0 never, 1 auto per warp, 2 always); pdl = programmatic dependent launch;
-        indexed = per-unique-vertex stage for MeshGrid / MeshModel (takes effect at the next set_object)."""
+        indexed = per-unique-vertex stage for MeshGrid / MeshModel (takes effect at the next set_object);
+        adaptive = stop launching the tile-path kernel after 8 consecutive calls that queued nothing."""
         L = _lib.lib()
         if tiny_max is not None:
             _lib.check(L.tina_raster_set_tuning(self._h, 0, int(tiny_max)))
@@ -221,7 +259,7 @@ class TriangleRaster:
             _lib.check(L.tina_raster_set_tuning(self._h, 3, int(collect_stats)))
         if profile is not None:
             _lib.check(L.tina_raster_set_tuning(self._h, 4, int(profile)))
-        for which, v in ((5, tighten), (6, precheck), (7, scan_max), (8, generic_vm), (9, balance), (10, pdl), (11, indexed)):
+        for which, v in ((5, tighten), (6, precheck), (7, scan_max), (8, generic_vm), (9, balance), (10, pdl), (11, indexed), (12, adaptive)):
             if v is not None:
                 _lib.check(L.tina_raster_set_tuning(self._h, which, int(v)))
 

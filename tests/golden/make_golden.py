@@ -180,6 +180,39 @@ def case_lights_materials():
     np.save(os.path.join(HERE, 'monkey_trans.npy'), trans)
 
 
+def case_gbuffers():
+    """ShaderGroup fan-out (shader.py:138-148, scene/raster.py:101-107): every G-buffer shader of
+    core/shader.py:21-109 as a post-shader of one smooth, textured object."""
+    ti = tina.ti
+    scene = tina.Scene((52, 44), smoothing=True, texturing=True)
+    res = scene.res
+    bufs = {
+        'const': (ti.field(int, res), lambda b: tina.ConstShader(b, 7)),
+        'position': (ti.Vector.field(3, float, res), tina.PositionShader),
+        'depth': (ti.field(float, res), tina.DepthShader),
+        'normal': (ti.Vector.field(3, float, res), tina.NormalShader),
+        'viewnormal': (ti.Vector.field(3, float, res), tina.ViewNormalShader),
+        'texcoord': (ti.Vector.field(2, float, res), tina.TexcoordShader),
+        'color': (ti.Vector.field(3, float, res), tina.ColorShader),
+        'chessboard': (ti.field(float, res), lambda b: tina.ChessboardShader(b, 8)),
+        'viewdir': (ti.Vector.field(3, float, res), tina.ViewdirShader),
+        'simple': (ti.field(float, res), tina.SimpleShader),
+    }
+    for name, (buf, make) in bufs.items():
+        scene.post_shaders.append(make(buf))
+    obj = tina.readobj(os.path.join(REF, 'assets/monkey.obj'))
+    scene.add_object(tina.MeshModel(obj), tina.Classic())
+    camera(scene, 52 / 44, back=(0.8, 0.4, 2.6))
+    for s in scene.post_shaders:
+        s.clear_buffer()
+    render_and_dump('gbuffer_shadergroup', scene, ['Classic()'])
+    path = os.path.join(HERE, 'gbuffer_shadergroup.npz')
+    d = dict(np.load(path))
+    for name, (buf, _) in bufs.items():
+        d['sink_' + name] = buf.to_numpy()
+    np.savez_compressed(path, **d)
+
+
 if __name__ == '__main__':
     np.seterr(all='ignore')
     case_monkey()
@@ -188,3 +221,4 @@ if __name__ == '__main__':
     case_edges()
     case_multi_object()
     case_lights_materials()
+    case_gbuffers()

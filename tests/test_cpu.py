@@ -147,3 +147,21 @@ def test_product_never_imports_oracle():
         if fn.endswith('.py'):
             assert 'oracle' not in open(os.path.join(pkg, fn)).read(), fn
     assert 'oracle' not in open(os.path.join(pkg, 'csrc', 'tina_b200.cu')).read().replace('the serial CPU restatement', '')
+
+
+def test_material_compile_shapes(tina):
+    """fold + hoist keeps the stock materials in the shapes the specialised shading kernels recognise,
+    with texture samples shared through prologue registers."""
+    from taichi_three_b200 import _lib as L
+    from taichi_three_b200.material import compile_material
+    img = np.zeros((4, 4, 3), np.uint8)
+    ops = lambda code: [i[0] for i in code]
+    b, a, e, p, _ = compile_material(tina.Diffuse())
+    assert ops(b) == [L.OP_CONST] and ops(a) == [L.OP_CONST] and not p
+    b, a, e, p, _ = compile_material(tina.Classic())
+    assert ops(b) == [L.OP_CONST] * 3 + [L.OP_PHONG, L.OP_MIX] and not p
+    b, a, e, p, tex = compile_material(tina.PBR(basecolor=tina.Texture(img), metallic=0.0, roughness=0.5))
+    assert ops(b) == [L.OP_REG, L.OP_REG, L.OP_CONST, L.OP_REG, L.OP_COOK, L.OP_MIX]
+    assert ops(p).count(L.OP_TEXTURE) == 1 and ops(a) == [L.OP_REG] and len(tex) == 1
+    b, a, e, p, _ = compile_material(tina.Classic(color=tina.Texture(img)))
+    assert ops(b) == [L.OP_CONST, L.OP_REG, L.OP_CONST, L.OP_PHONG, L.OP_MIX] and ops(p).count(L.OP_TEXTURE) == 1

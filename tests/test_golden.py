@@ -115,3 +115,24 @@ def test_camera_helpers_match_reference(tina):
     L = tina.Lighting()
     L.add_light(dir=[1, 2, 3], color=[0.9, 0.9, 0.9])
     assert np.array_equal(L.light_dirs[0], g['light_dirs'][0]) and np.array_equal(L.light_colors[0], g['light_colors'][0])
+
+
+SINKS = {'const': (0, (7, 7, 7)), 'position': (1, None), 'depth': (2, None), 'normal': (3, None), 'viewnormal': (4, None),
+         'texcoord': (5, None), 'color': (6, None), 'chessboard': (7, (8, 0, 0)), 'viewdir': (8, None), 'simple': (9, None)}
+
+
+def test_oracle_gbuffer_sinks_match_reference_shadergroup(tina, O):
+    """core/shader.py:21-109 through ShaderGroup (shader.py:138-148): the oracle's sinks against the
+    reference's own sources under the shim."""
+    g = np.load(os.path.join(GOLDEN, 'gbuffer_shadergroup.npz'))
+    W, H = (int(v) for v in g['res'])
+    flags = int(g['flags'])
+    occup, depth, _, _ = O.render_occup(g['verts0'], g['W2V'], W, H, flags, g['bias'])
+    assert np.array_equal(occup, g['occup0']) and np.array_equal(depth, g['depth'])
+    for name, (kind, param) in SINKS.items():
+        ref = g['sink_' + name].astype(np.float32).reshape(W, H, -1)
+        out = np.zeros_like(ref)
+        O.render_gbuffer(kind, g['verts0'], g['norms0'], g['coors0'], occup, depth, g['W2V'], g['V2W'], W, H, flags, out,
+                         param or (0, 0, 0), g['bias'])
+        assert np.abs(out - ref).max() <= 1e-6 * max(1.0, np.abs(ref).max()), name
+        assert np.abs(ref).max() > 0, name

@@ -491,3 +491,79 @@ def test_indexed_vertex_stage_equals_expanded_path(tina, O, case):
     for a, b in zip(res[0], res[1]):
         assert np.array_equal(a, b)
     assert ((res[0][0] & 0xffffffff) != 0).sum() > 2000
+
+
+def test_adaptive_tile_path_skipping_stays_exact(tina, O):
+    """After 8 consecutive frames without large faces the idle tile-path kernel is no longer launched and
+    k_raster_faces walks large faces itself.  A frame that suddenly contains big triangles must still be
+    exact, and so must the frames after it (tile path back on)."""
+    import torch
+    W, H = 256, 160
+    view, proj = scenes.default_camera(W / H)
+    small = scenes.soup(20000, W, H, s=0.01, seed=3)
+    big = np.concatenate([scenes.soup(3000, W, H, s=0.01, seed=4),
+                          np.float32([[[-1.5, -1, 0.3], [1.5, -1, 0.3], [0, 1.2, -0.2]], [[-1, 0.8, 0.5], [-1, -0.8, 0.5], [1.1, 0, -0.4]]]),
+                          scenes.soup(300, W, H, s=0.15, seed=6)]).astype(np.float32)
+    scene = tina.Scene((W, H), maxfaces=len(small))
+    mesh = tina.SimpleMesh(maxfaces=len(small))
+    scene.add_object(mesh)
+    scene.engine.set_camera(view, proj)
+    refs = {}
+    for name, tri in (('small', small), ('big', big)):
+        refs[name] = O.render_scene([(tri, None, None, tina.Diffuse())], W, H, view, proj, scene.lighting, _flags(O))
+    seq = ['small'] * 12 + ['big', 'big', 'small', 'big'] + ['small'] * 10 + ['big']
+    for name in seq:
+        mesh.set_face_verts(small if name == 'small' else big)
+        scene.render()
+        torch.cuda.synchronize()
+        _check_frame(scene, refs[name])
+
+
+def test_gbuffer_shadergroup_matches_reference_golden(tina):
+    """§8f row 1: G-buffer shaders + ShaderGroup fan-out on the CUDA path against the golden produced by
+    the reference's own ShaderGroup (tests/golden/make_golden.py::case_gbuffers)."""
+    import os
+    import torch
+    from test_golden import GOLDEN, SINKS, _lighting
+    g = np.load(os.path.join(GOLDEN, 'gbuffer_shadergroup.npz'))
+    W, H = (int(v) for v in g['res'])
+    flags = int(g['flags'])
+    engine = tina.Engine((W, H))
+    engine.W2V[None], engine.V2W[None], engine.bias[None] = g['W2V'], g['V2W'], g['bias']
+    raster = tina.TriangleRaster(engine, smoothing=bool(flags & 1), texturing=bool(flags & 2))
+    classes = {'const': lambda b: tina.ConstShader(b, 7), 'position': tina.PositionShader, 'depth': tina.DepthShader,
+               'normal': tina.NormalShader, 'viewnormal': tina.ViewNormalShader, 'texcoord': tina.TexcoordShader,
+               'color': tina.ColorShader, 'chessboard': lambda b: tina.ChessboardShader(b, 8), 'viewdir': tina.ViewdirShader,
+               'simple': tina.SimpleShader}
+    bufs, shaders = {}, []
+    img = tina.Field(torch.zeros((W, H, 3), device='cuda'))
+    shaders.append(tina.Shader(img, _lighting(tina, g), tina.Classic()))
+    for name in SINKS:
+        ref = g['sink_' + name]
+        t = torch.zeros(ref.shape, device='cuda', dtype=torch.int32 if ref.dtype.kind == 'i' else torch.float32)
+        bufs[name] = t
+        shaders.append(classes[name](tina.Field(t)))
+    mesh = tina.SimpleMesh()
+    mesh.set_face_verts(g['verts0'])
+    mesh.set_face_norms(g['norms0'])
+    mesh.set_face_coors(g['coors0'])
+    engine.clear_depth()
+    raster.set_object(mesh)
+    raster.render_occup()
+    raster.render_color(tina.ShaderGroup(shaders))
+    torch.cuda.synchronize()
+    assert np.array_equal(raster.occup.to_numpy(), g['occup0'])
+    assert np.abs(img.to_numpy() - g['image_pre_tonemap']).max() <= COLOR_TOL
+    for name in SINKS:
+        ref = g['sink_' + name].astype(np.float64)
+        out = bufs[name].cpu().numpy().astype(np.float64)
+        assert np.abs(out - ref).max() <= 1e-5 * max(1.0, np.abs(ref).max()), name
+    # the same through the indexed (MeshModel) path
+    scene = tina.Scene((W, H), smoothing=True, texturing=True)
+    nb = torch.zeros((W, H, 3), device='cuda')
+    scene.post_shaders.append(tina.NormalShader(tina.Field(nb)))
+    scene.add_object(tina.MeshModel(scenes.load_monkey()), tina.Classic())
+    scene.engine.W2V[None], scene.engine.V2W[None] = g['W2V'], g['V2W']
+    scene.render()
+    torch.cuda.synchronize()
+    assert np.abs(nb.cpu().numpy() - g['sink_normal']).max() <= 1e-6
