@@ -158,6 +158,12 @@ int tina_raster_render_occup(TinaRaster *r, void *stream);
 /* triangle.py:134-153 + shader.py:119-131 + lighting.py:84-98; image [W,H,3] f32 */
 int tina_raster_render_color(TinaRaster *r, const TinaMaterial *mat_host, const TinaLighting *light_host,
                              float *image, uint32_t flags, const float *bg_host, void *stream);
+/* render_color restricted to pixels [first_pixel, first_pixel + npixels) (first_pixel a multiple of 256) of
+ * the CURRENT face arrays with an explicit id offset: after a sort-last key composite every rank shades
+ * one screen strip from the replicated attributes (face_base = 0). */
+int tina_raster_render_color_range(TinaRaster *r, const TinaMaterial *mat_host, const TinaLighting *light_host,
+                                   float *image, uint32_t flags, const float *bg_host, int64_t first_pixel, int64_t npixels,
+                                   uint32_t face_base, void *stream);
 /* G-buffer sinks of core/shader.py:21-109 for the current object (ShaderGroup fan-out, shader.py:138-148):
  * writes `ncomp` (1..3) float32 (or int32 if out_is_int) values per pixel where the object is visible,
  * out[(x*H + y)*ncomp + k].  param_host: ConstShader value (3 floats) / ChessboardShader size (1 float). */

@@ -63,6 +63,8 @@ SIGNATURES = {
     'tina_raster_set_faces_grid': (_i, [_vp, _vp, _i, _i, _fp, _fp, _u32, _vp]),
     'tina_raster_render_occup': (_i, [_vp, _vp]),
     'tina_raster_render_color': (_i, [_vp, C.POINTER(TinaMaterial), C.POINTER(TinaLighting), _vp, _u32, _fp, _vp]),
+    'tina_raster_render_color_range': (_i, [_vp, C.POINTER(TinaMaterial), C.POINTER(TinaLighting), _vp, _u32, _fp, _i64, _i64,
+                                             _u32, _vp]),
     'tina_raster_render_gbuffer': (_i, [_vp, _i, _vp, _i, _i, _fp, _vp]),
     'tina_raster_occup': (_i, [_vp, _vp, _vp]),
     'tina_raster_buffers': (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i64)]),

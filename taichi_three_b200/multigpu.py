@@ -53,6 +53,54 @@ def composite_min(keys, group=None):
     return keys
 
 
+def strip_range(npix, rank, world):
+    """Contiguous pixel strip [lo, hi) of `rank` (x-major pixel indices, multiples of 256)."""
+    nblk = (npix + 255) // 256
+    per = (nblk + world - 1) // world
+    return min(rank * per * 256, npix), min((rank + 1) * per * 256, npix)
+
+
+def render_sort_last_replicated(engine, raster, verts, norms, coors, shader, bgcolor=0.0, group=None):
+    """Sort-last frame with REPLICATED face attributes (every rank holds all N faces, C5: 4.8 GB):
+    rank r rasterises faces face_range(N, r, G) with global ids, the keys are MIN-reduce-scattered so
+    rank r ends up with the final keys of screen strip r (1/G of the all-reduce traffic), shades that
+    strip from the full attribute arrays, and the image strips are all-gathered.  Bit-identical to one
+    GPU.  Needs W*H divisible by 256*G (else falls back to the all-reduce composite)."""
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    N = verts.shape[0]
+    lo, hi = face_range(N, rank, world)
+    npix = engine.res[0] * engine.res[1]
+    engine.clear_depth()
+    engine.set_face_base(lo)
+    raster.set_face_verts(verts[lo:hi])
+    if raster.smoothing:
+        raster.set_face_norms(norms[lo:hi])
+    if raster.texturing:
+        raster.set_face_coors(coors[lo:hi])
+    raster.render_occup()
+    keys = engine.keys.view(-1)
+    img = shader.img.to_torch() if hasattr(shader.img, 'to_torch') else shader.img
+    # the full arrays for shading (ids in the keys are global)
+    raster.set_face_verts(verts)
+    if raster.smoothing:
+        raster.set_face_norms(norms)
+    if raster.texturing:
+        raster.set_face_coors(coors)
+    if world > 1 and npix % (256 * world) == 0:
+        p_lo, p_hi = strip_range(npix, rank, world)
+        strip = torch.empty(p_hi - p_lo, dtype=torch.int64, device=keys.device)
+        dist.reduce_scatter_tensor(strip, keys, op=dist.ReduceOp.MIN, group=group)
+        keys[p_lo:p_hi] = strip
+        raster.render_color_range(shader, p_lo, p_hi - p_lo, face_base=0, fill_bg=bgcolor)
+        flat = img.view(-1)
+        dist.all_gather_into_tensor(flat, flat[p_lo * 3:p_hi * 3].clone(), group=group)
+    else:
+        composite_min(keys, group)
+        raster.render_color_range(shader, 0, npix, face_base=0, fill_bg=bgcolor)
+    return img
+
+
 def render_sort_last(engine, raster, verts, norms, coors, shader, bgcolor=0.0, group=None):
     """One sort-last frame.  `verts/norms/coors` are this rank's CUDA slices of the global face arrays
     (range = face_range(N, rank, world)); returns the composited [W, H, 3] image on every rank."""

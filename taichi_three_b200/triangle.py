@@ -166,6 +166,20 @@ class TriangleRaster:
                 _lib.check(rc)
             self._mat_keep = keep
 
+    def render_color_range(self, shader, first_pixel, npixels, face_base=0, fill_bg=None):
+        """Shade pixels [first_pixel, first_pixel + npixels) of the current face arrays, ids offset by
+        face_base (sort-last: one screen strip per rank after the key composite)."""
+        if not isinstance(shader, Shader):
+            raise NotImplementedError('render_color_range takes a single Shader')
+        t = shader.img.to_torch() if hasattr(shader.img, 'to_torch') else shader.img
+        mat, keep = self._material_struct(shader.material)
+        flags = _lib.TINA_COLOR_FILL_BG if fill_bg is not None else 0
+        bg = _fp(np.broadcast_to(np.asarray(fill_bg if fill_bg is not None else 0, dtype=np.float32), (3,)))
+        _lib.check(_lib.lib().tina_raster_render_color_range(self._h, mat, shader.lighting.struct_ref(), C.c_void_p(t.data_ptr()),
+                                                             flags, bg, int(first_pixel), int(npixels), int(face_base),
+                                                             _stream(self._dev_index)))
+        self._mat_keep = keep
+
     def _render_sink(self, s, st):
         """G-buffer shaders (shader.py:21-109) for the current object."""
         t = s.img.to_torch() if hasattr(s.img, 'to_torch') else s.img

@@ -79,3 +79,12 @@ def test_sort_last_composite_equals_single_pass_gloo(tmp_path, O):
     assert np.array_equal(r['occup'], ref_occup)
     assert int(r['owned'][0]) == int((ref_occup >= 0).sum())
     assert not np.isin(ref_occup, np.arange(1500, 1700)).any()
+
+
+def test_strip_ranges_tile_the_screen():
+    from taichi_three_b200 import multigpu as M
+    for npix, w in ((7680 * 4320, 8), (1920 * 1080, 8), (1000, 3), (256, 4), (3840 * 2160, 2)):
+        r = [M.strip_range(npix, k, w) for k in range(w)]
+        assert r[0][0] == 0 and r[-1][1] == npix
+        assert all(r[i][1] == r[i + 1][0] for i in range(w - 1))
+        assert all(lo % 256 == 0 for lo, hi in r if lo < npix)
