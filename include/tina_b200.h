@@ -211,6 +211,8 @@ int tina_raster_kernel_times(TinaRaster *r, float *ms5_host);
 /* ---- frame glue (scene/raster.py:176,202-203) -------------------------------- */
 int tina_image_fill(float *image, int64_t npixels, const float *rgb_host, void *stream);
 int tina_image_tonemap(float *image, int64_t nfloats, void *stream);
+/* TAA accumulation, util/accumator.py:16-23: acc = acc * (1 - 1/count) + src * (1/count), count >= 1 */
+int tina_image_accumulate(float *acc, const float *src, int64_t nfloats, int count, void *stream);
 
 #ifdef __cplusplus
 }

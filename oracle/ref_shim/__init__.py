@@ -242,6 +242,13 @@ class IntRef(builtins.int):
         o.field, o.idx = field, idx
         return o
 
+    # a runtime i32 value: Taichi's `/` is a true division in default_fp (f32), not Python's f64
+    def __truediv__(self, o):
+        return F32(builtins.int(self)) / (F32(o) if isinstance(o, (builtins.int, IntRef)) else o)
+
+    def __rtruediv__(self, o):
+        return (F32(o) if isinstance(o, (builtins.int, IntRef)) else o) / F32(builtins.int(self))
+
 
 def _dtype(dt):
     if dt in (builtins.float, F32, 'f32') or getattr(dt, '_shim_kind', None) == 'f':

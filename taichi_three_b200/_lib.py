@@ -73,6 +73,7 @@ SIGNATURES = {
     'tina_raster_kernel_times': (_i, [_vp, _fp]),
     'tina_image_fill': (_i, [_vp, _i64, _fp, _vp]),
     'tina_image_tonemap': (_i, [_vp, _i64, _vp]),
+    'tina_image_accumulate': (_i, [_vp, _vp, _i64, _i, _vp]),
 }
 
 _lib = None

@@ -21,8 +21,26 @@ class _ObjInfo:
         self.material, self.raster = material, raster
 
 
+class Accumator:
+    """TAA accumulation buffer (reference tina/util/accumator.py:5-23)."""
+
+    def __init__(self, res, device):
+        self.img = Field(torch.zeros((res[0], res[1], 3), dtype=torch.float32, device=device))
+        self.count = [0]
+
+    def clear(self):
+        self.count[0] = 0
+        self.img.to_torch().zero_()
+
+    def update(self, src):
+        self.count[0] += 1
+        a, s = self.img.to_torch(), src.to_torch()
+        _lib.check(_lib.lib().tina_image_accumulate(C.c_void_p(a.data_ptr()), C.c_void_p(s.data_ptr()), a.numel(),
+                                                    self.count[0], _stream()))
+
+
 class Scene:
-    UNSUPPORTED = ('taa', 'ibl', 'ssr', 'ssao', 'fxaa', 'blooming')
+    UNSUPPORTED = ('ibl', 'ssr', 'ssao', 'fxaa', 'blooming')
 
     def __init__(self, res_x=512, res_y=None, **options):
         self.engine = Engine(res_x, res_y)
@@ -31,6 +49,7 @@ class Scene:
         for key in self.UNSUPPORTED:
             if options.get(key, False):
                 raise NotImplementedError(f'Scene option {key}=True is outside the B200 triangle-raster path')
+        self.taa = options.get('taa', False)
         self.tonemap = options.get('tonemap', True)
         self.bgcolor = options.get('bgcolor', 0)
         self.lighting = Lighting()
@@ -42,6 +61,8 @@ class Scene:
         self.shaders = {}
         self.objects = {}
         self.pp_img = self.image
+        if self.taa:
+            self.accum = Accumator(self.res, self.engine.device)
         # raster.py:90-93
         self.lighting.add_light(dir=[1, 2, 3], color=[0.9, 0.9, 0.9])
         self.lighting.set_ambient_light([0.1, 0.1, 0.1])
@@ -82,6 +103,8 @@ class Scene:
     def render(self):
         """raster.py:168-207.  image.fill(bg) is fused into the first object's shading pass and, for
         single-object scenes, so is the ACES tonemap; results are identical to the separate passes."""
+        if self.taa:  # raster.py:173-174: jittered sample position, centred on the first frame
+            self.engine.randomize_bias(self.accum.count[0] == 0)
         self.engine.clear_depth()
         for s in self.pre_shaders + self.post_shaders:
             s.clear_buffer()
@@ -103,19 +126,25 @@ class Scene:
         if self.tonemap and not fuse_tm:
             t = self.image.to_torch()
             _lib.check(_lib.lib().tina_image_tonemap(C.c_void_p(t.data_ptr()), t.numel(), _stream()))
+        if self.taa:  # raster.py:206-207
+            self.accum.update(self.pp_img)
 
     @property
     def img(self):
-        return self.pp_img
+        return self.accum.img if self.taa else self.pp_img
 
     def input(self, gui):  # raster.py:216-228
         if not hasattr(self, 'control'):
             from .control import Control
             self.control = Control(gui)
-        return self.control.apply_camera(self.engine)
+        changed = self.control.apply_camera(self.engine)
+        if changed:
+            self.clear()
+        return changed
 
-    def clear(self):
-        pass
+    def clear(self):  # raster.py:230-232
+        if self.taa:
+            self.accum.clear()
 
     def load_gltf(self, path):  # raster.py:234-241
         from .assimp import readgltf

@@ -136,3 +136,31 @@ def test_oracle_gbuffer_sinks_match_reference_shadergroup(tina, O):
                          param or (0, 0, 0), g['bias'])
         assert np.abs(out - ref).max() <= 1e-6 * max(1.0, np.abs(ref).max()), name
         assert np.abs(ref).max() > 0, name
+
+
+def test_accumulator_formula_matches_reference_source():
+    """util/accumator.py under the shim == acc * (1 - 1/count) + src * (1/count) in f32 (what k_accumulate does)."""
+    if not os.path.isdir('/root/reference/tina'):
+        pytest.skip('reference tree not present (GPU box)')
+    from oracle import ref_shim
+    ref = ref_shim.load_tina('/root/reference')
+    import importlib
+    acc_mod = importlib.import_module('tina.util.accumator') if False else None
+    import sys
+    sys.meta_path  # noqa
+    rng = np.random.default_rng(0)
+    # the shim only preloads the raster path; load the accumulator module the same way
+    import types
+    src_code = open('/root/reference/tina/util/accumator.py').read().replace('from ..common import *', '')
+    ns = dict(vars(sys.modules['tina.common']))
+    exec(compile(src_code, 'accumator.py', 'exec'), ns)
+    A = ns['Accumator']((5, 4))
+    mine = np.zeros((5, 4, 3), np.float32)
+    img = sys.modules['taichi'].Vector.field(3, float, (5, 4))
+    for k in range(1, 5):
+        frame = rng.random((5, 4, 3)).astype(np.float32)
+        img.from_numpy(frame)
+        A.update(img)
+        inv = np.float32(1) / np.float32(k)
+        mine = mine * (np.float32(1) - inv) + frame * inv
+        assert np.array_equal(A.img.to_numpy(), mine)

@@ -567,3 +567,32 @@ def test_gbuffer_shadergroup_matches_reference_golden(tina):
     scene.render()
     torch.cuda.synchronize()
     assert np.abs(nb.cpu().numpy() - g['sink_normal']).max() <= 1e-6
+
+
+def test_taa_accumulation(tina, O):
+    """§8f row 2: Scene(taa=True) = jittered bias + Accumator.update (util/accumator.py:16-23);
+    every jittered frame must still match the oracle, and the running mean uses the reference's f32 ops."""
+    import torch
+    W, H = 96, 72
+    view, proj = scenes.default_camera(W / H)
+    tri = scenes.soup(800, W, H, s=0.08, seed=12)
+    scene = tina.Scene((W, H), taa=True)
+    mesh = tina.SimpleMesh()
+    mesh.set_face_verts(tri)
+    scene.add_object(mesh)
+    scene.engine.set_camera(view, proj)
+    acc = np.zeros((W, H, 3), np.float32)
+    for k in range(1, 6):
+        scene.render()
+        torch.cuda.synchronize()
+        bias = scene.engine.bias.to_numpy()
+        assert (k == 1 and np.array_equal(bias, np.float32([0.5, 0.5]))) or (k > 1 and 0 <= bias.min() and bias.max() < 1)
+        ref = O.render_scene([(tri, None, None, tina.Diffuse())], W, H, view, proj, scene.lighting, _flags(O), bias=bias)
+        assert np.array_equal(scene.engine.depth.to_numpy(), ref['depth'])
+        frame = scene.pp_img.to_numpy()
+        assert np.abs(frame - ref['image']).max() <= COLOR_TOL
+        inv = np.float32(1) / np.float32(k)
+        acc = acc * (np.float32(1) - inv) + frame * inv
+        assert np.array_equal(scene.img.to_numpy(), acc)
+    scene.clear()
+    assert scene.accum.count[0] == 0 and float(scene.img.to_numpy().max()) == 0.0
