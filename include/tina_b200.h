@@ -208,6 +208,20 @@ int tina_raster_stats(TinaRaster *r, int64_t *out6_host);
  * [4] k_render_color ([2] unused; -1 = never recorded); needs tuning knob 4; synchronises on the events */
 int tina_raster_kernel_times(TinaRaster *r, float *ms5_host);
 
+/* ---- ParticleRaster (core/particle.py:4-161): sphere splats on the same Engine (shared depth / ids) ---- */
+typedef struct TinaPars TinaPars;
+/* flags: 1 = coloring, 2 = clipping (particle.py:6-12) */
+int tina_pars_create(TinaPars **out, TinaEngine *e, int64_t maxpars, uint32_t flags);
+int tina_pars_destroy(TinaPars *r);
+/* set_object (particle.py:64-76) for SimpleParticles (+ParsTransform, pars/trans.py:22-31): verts [N,3], sizes [N],
+ * colors [N,3] or NULL; trans_host (4x4) / scale optional; borrow=1 aliases the caller's buffers */
+int tina_pars_set(TinaPars *r, const float *verts, const float *sizes, const float *colors, int64_t npars,
+                  const float *trans_host, float scale, int borrow, void *stream);
+int tina_pars_render_occup(TinaPars *r, void *stream);                    /* particle.py:78-127 */
+int tina_pars_render_color(TinaPars *r, const TinaMaterial *mat_host, const TinaLighting *light_host, float *image,
+                           uint32_t flags, const float *bg_host, void *stream); /* particle.py:129-161 */
+int tina_pars_occup(TinaPars *r, int32_t *occup, void *stream);
+
 /* ---- frame glue (scene/raster.py:176,202-203) -------------------------------- */
 int tina_image_fill(float *image, int64_t npixels, const float *rgb_host, void *stream);
 int tina_image_tonemap(float *image, int64_t nfloats, void *stream);

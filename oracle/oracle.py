@@ -75,10 +75,8 @@ def face_setup(verts, W2V, W, H, flags=CULLING | CLIPPING):
     return out, bbox
 
 
-def render_color(verts, norms, coors, occup, W2V, V2W, W, H, flags, material, lighting, image, bias=(0.5, 0.5),
-                 parallel=True):
-    """Shades pixels with occup != -1 into `image` ([W,H,3] f32, modified in place and returned).
-    `material` is a taichi_three_b200 material node graph, `lighting` a taichi_three_b200.Lighting."""
+def _material_pod(material):
+    """the plain (unfolded, unhoisted) TinaMaterial program + host texture pointers"""
     from taichi_three_b200 import _lib as P
     from taichi_three_b200.material import flatten_material
     brdf, amb, emi, textures = flatten_material(material)
@@ -93,6 +91,36 @@ def render_color(verts, norms, coors, occup, W2V, V2W, W, H, flags, material, li
     for i, t in enumerate(tex_arrays):
         texptrs[i] = t.ctypes.data
         m.tex_w[i], m.tex_h[i], m.tex_c[i] = t.shape
+    return m, texptrs, tex_arrays
+
+
+def pars_occup(verts, sizes, W2V, V2W, W, H, clipping=True, bias=(0.5, 0.5), depth=None):
+    """core/particle.py:78-127 -> (occup, depth)"""
+    verts, sizes = _f(verts).reshape(-1, 3), _f(sizes).reshape(-1)
+    depth = clear_depth(W, H) if depth is None else np.ascontiguousarray(depth, dtype=np.int32).copy()
+    occup = np.empty((W, H), dtype=np.int32)
+    lib().orc_pars_occup(_p(verts), _p(sizes), C.c_int64(len(verts)), _p(_f(W2V).reshape(16)), _p(_f(V2W).reshape(16)),
+                         _p(_f(bias)), W, H, C.c_uint32(2 if clipping else 0), _p(depth), _p(occup))
+    return occup, depth
+
+
+def pars_color(verts, sizes, colors, occup, W2V, V2W, W, H, material, lighting, image, bias=(0.5, 0.5)):
+    """core/particle.py:129-161; shades pixels with occup != -1 into image (in place)."""
+    m, texptrs, keep = _material_pod(material)
+    L = lighting.struct()
+    verts, sizes = _f(verts).reshape(-1, 3), _f(sizes).reshape(-1)
+    colors = _f(colors).reshape(-1, 3) if colors is not None else None
+    lib().orc_pars_color(_p(verts), _p(sizes), _p(colors), _p(np.ascontiguousarray(occup, dtype=np.int32)),
+                         _p(_f(W2V).reshape(16)), _p(_f(V2W).reshape(16)), _p(_f(bias)), W, H, C.byref(m), texptrs, C.byref(L),
+                         _p(image))
+    return image
+
+
+def render_color(verts, norms, coors, occup, W2V, V2W, W, H, flags, material, lighting, image, bias=(0.5, 0.5),
+                 parallel=True):
+    """Shades pixels with occup != -1 into `image` ([W,H,3] f32, modified in place and returned).
+    `material` is a taichi_three_b200 material node graph, `lighting` a taichi_three_b200.Lighting."""
+    m, texptrs, tex_arrays = _material_pod(material)
     L = lighting.struct()
     verts = _f(verts).reshape(-1, 9)
     norms = _f(norms).reshape(-1, 9) if norms is not None else None

@@ -477,7 +477,8 @@ def make_transformations():
 
 NEEDED = ['common', 'advans', 'util.matrix', 'matr.nodes', 'matr.material', 'core.engine', 'core.lighting',
           'core.shader', 'core.triangle', 'mesh.base', 'mesh.simple', 'mesh.model', 'mesh.grid', 'mesh.trans',
-          'mesh.cull', 'mesh.norm', 'postp.tonemap', 'assimp.obj', 'assimp.gltf', 'scene.raster']
+          'mesh.cull', 'mesh.norm', 'postp.tonemap', 'assimp.obj', 'assimp.gltf', 'core.particle', 'pars.base',
+          'pars.simple', 'pars.trans', 'scene.raster']
 
 
 def load_tina(ref_root='/root/reference'):

@@ -514,6 +514,117 @@ void orc_render_gbuffer(const float *verts, const float *norms, const float *coo
         }
 }
 
+/* ---- ParticleRaster (core/particle.py) -------------------------------------------------- */
+static void mapply_dir_n(const float *M, float d0, float d1, float d2, float *r) { /* common.py:186-189 + normalized */
+    float d[3] = {d0, d1, d2}, rw;
+    mapply(M, d, 0.0f, r, &rw);
+    normalize3(r);
+}
+
+/* particle.py:78-127, serial order; flags: 2 = clipping.  depth persists, occup is reset. */
+void orc_pars_occup(const float *verts, const float *sizes, int64_t npars, const float *W2V, const float *V2W,
+                    const float *bias, int W, int H, uint32_t flags, int32_t *depth, int32_t *occup) {
+    for (int64_t i = 0; i < (int64_t)W * H; i++) occup[i] = -1;
+    float DXl[3], DYl[3];
+    mapply_dir_n(V2W, 1, 0, 0, DXl);
+    mapply_dir_n(V2W, 0, 1, 0, DYl);
+    float res[2] = {(float)W, (float)H};
+    int resi[2] = {W, H};
+    for (int64_t f = 0; f < npars; f++) {
+        const float *Al = verts + f * 3;
+        float Rl = sizes[f], Av[3], t[3], q[3];
+        mapply_pos(W2V, Al, Av);
+        if ((flags & 2u) && !(-1.0f <= Av[2] && Av[2] <= 1.0f)) continue;
+        float Rv[2];
+        for (int k = 0; k < 3; k++) q[k] = Al[k] + DXl[k] * Rl;
+        mapply_pos(W2V, q, t);
+        Rv[0] = t[0] - Av[0];
+        for (int k = 0; k < 3; k++) q[k] = Al[k] + DYl[k] * Rl;
+        mapply_pos(W2V, q, t);
+        Rv[1] = t[1] - Av[1];
+        float Bv[4][2] = {{Av[0] - Rv[0], Av[1] - 0.0f}, {Av[0] + Rv[0], Av[1] + 0.0f}, {Av[0] - 0.0f, Av[1] - Rv[1]}, {Av[0] + 0.0f, Av[1] + Rv[1]}};
+        float b[4][2];
+        for (int j = 0; j < 4; j++)
+            for (int k = 0; k < 2; k++) b[j][k] = (Bv[j][k] * 0.5f + 0.5f) * res[k];
+        int32_t bot[2], top[2];
+        for (int k = 0; k < 2; k++) {
+            int32_t lo = ifloor_(fminf(b[0][k], b[2][k])), hi = iceil_(fmaxf(b[1][k], b[3][k]));
+            bot[k] = lo > 0 ? lo : 0;
+            top[k] = hi < resi[k] - 1 ? hi : resi[k] - 1;
+        }
+        int32_t d = f2i(Av[2] * MAXDEPTH_F);
+        for (int32_t x = bot[0]; x <= top[0]; x++)
+            for (int32_t y = bot[1]; y <= top[1]; y++) {
+                float p[2] = {(float)x + bias[0], (float)y + bias[1]};
+                float Pv[3] = {p[0] / res[0] * 2.0f - 1.0f, p[1] / res[1] * 2.0f - 1.0f, Av[2]}, Pl[3];
+                mapply_pos(V2W, Pv, Pl);
+                float e[3] = {Pl[0] - Al[0], Pl[1] - Al[1], Pl[2] - Al[2]};
+                if ((e[0] * e[0] + e[1] * e[1]) + e[2] * e[2] > Rl * Rl) continue;
+                int64_t P = (int64_t)x * H + y;
+                if (depth[P] > d) {
+                    depth[P] = d;
+                    occup[P] = (int32_t)f;
+                }
+            }
+    }
+}
+
+/* particle.py:129-161 + shader.py:119-131 + lighting.py:84-98 */
+void orc_pars_color(const float *verts, const float *sizes, const float *colors, const int32_t *occup, const float *W2V,
+                    const float *V2W, const float *bias, int W, int H, const TinaMaterial *mat,
+                    const float *const *textures, const TinaLighting *L, float *image) {
+    float Zl[3];
+    mapply_dir_n(V2W, 0, 0, 1, Zl);
+    for (int x = 0; x < W; x++)
+        for (int y = 0; y < H; y++) {
+            int64_t P = (int64_t)x * H + y;
+            int32_t f = occup[P];
+            if (f == -1) continue;
+            const float *Al = verts + (int64_t)f * 3;
+            float Rl = sizes[f], Av[3];
+            mapply_pos(W2V, Al, Av);
+            float p[2] = {(float)x + bias[0], (float)y + bias[1]};
+            float Pv[3] = {p[0] / (float)W * 2.0f - 1.0f, p[1] / (float)H * 2.0f - 1.0f, Av[2]}, Pl[3], Dl[3];
+            mapply_pos(V2W, Pv, Pl);
+            for (int k = 0; k < 3; k++) Dl[k] = (Pl[k] - Al[k]) / Rl;
+            float t = sqrtf(1.0f - dot3(Dl, Dl));
+            for (int k = 0; k < 3; k++) Dl[k] = Dl[k] - Zl[k] * t;
+            normalize3(Dl);
+            ShadeInputs in;
+            for (int k = 0; k < 3; k++) {
+                in.normal[k] = Dl[k];
+                in.pos[k] = Al[k] + Dl[k] * Rl;
+                in.texcoord[k] = 0.0f;
+                in.color[k] = colors ? colors[(int64_t)f * 3 + k] : 1.0f;
+            }
+            float q[3] = {Pv[0], Pv[1], -1.0f}, ro[3], ro1[3], rd[3];
+            mapply_pos(V2W, q, ro);
+            q[2] = 1.0f;
+            mapply_pos(V2W, q, ro1);
+            for (int k = 0; k < 3; k++) rd[k] = ro1[k] - ro[k];
+            normalize3(rd);
+            float viewdir[3] = {-rd[0], -rd[1], -rd[2]};
+            float res[3] = {0, 0, 0}, tmp[3], zero[3] = {0, 0, 0};
+            run_program(mat, textures, mat->n_brdf + mat->n_ambient, mat->n_emission, &in, zero, zero, zero, tmp);
+            for (int k = 0; k < 3; k++) res[k] += tmp[k];
+            run_program(mat, textures, mat->n_brdf, mat->n_ambient, &in, zero, zero, zero, tmp);
+            for (int k = 0; k < 3; k++) res[k] += L->ambient[k] * tmp[k];
+            for (int l = 0; l < L->nlights; l++) {
+                float ld[3];
+                for (int k = 0; k < 3; k++) ld[k] = L->dirs[l][k] - in.pos[k] * L->dirs[l][3];
+                float dist = sqrtf(dot3(ld, ld));
+                for (int k = 0; k < 3; k++) ld[k] = ld[k] / dist;
+                float cos_i = dot3(in.normal, ld);
+                if (cos_i > 0) {
+                    float d2 = dist * dist;
+                    run_program(mat, textures, 0, mat->n_brdf, &in, in.normal, ld, viewdir, tmp);
+                    for (int k = 0; k < 3; k++) res[k] += cos_i * (L->colors[l][k] / d2) * tmp[k];
+                }
+            }
+            for (int k = 0; k < 3; k++) image[P * 3 + k] = res[k];
+        }
+}
+
 /* ---- mesh providers feeding set_object ------------------------------------------ */
 
 /* mesh/grid.py:26-35 MeshGrid.pre_compute; pos, nrm: [nx][ny][3] */

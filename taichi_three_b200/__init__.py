@@ -17,6 +17,7 @@ from .mesh import (MAX, SimpleMesh, MeshModel, MeshGrid, MeshTransform, MeshFlip
                    MeshFlipNormal, MeshFlatNormal, MeshSmoothNormal, MeshEditBase)
 from .engine import Engine
 from .triangle import TriangleRaster
+from .particle import ParticleRaster, SimpleParticles, ParsTransform
 from .scene import Scene
 from .control import Control, RotationStep
 from .field import Field

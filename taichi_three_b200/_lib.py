@@ -71,6 +71,12 @@ SIGNATURES = {
     'tina_raster_set_tuning': (_i, [_vp, _i, _i]),
     'tina_raster_stats': (_i, [_vp, C.POINTER(_i64)]),
     'tina_raster_kernel_times': (_i, [_vp, _fp]),
+    'tina_pars_create': (_i, [C.POINTER(_vp), _vp, _i64, _u32]),
+    'tina_pars_destroy': (_i, [_vp]),
+    'tina_pars_set': (_i, [_vp, _vp, _vp, _vp, _i64, _fp, _f, _i, _vp]),
+    'tina_pars_render_occup': (_i, [_vp, _vp]),
+    'tina_pars_render_color': (_i, [_vp, C.POINTER(TinaMaterial), C.POINTER(TinaLighting), _vp, _u32, _fp, _vp]),
+    'tina_pars_occup': (_i, [_vp, _vp, _vp]),
     'tina_image_fill': (_i, [_vp, _i64, _fp, _vp]),
     'tina_image_tonemap': (_i, [_vp, _i64, _vp]),
     'tina_image_accumulate': (_i, [_vp, _vp, _i64, _i, _vp]),

@@ -304,10 +304,11 @@ _F = np.float32
 _INV_PI = _F(0.3183098861837907)  # Python folds `1 / ti.pi` in f64 (material.py:393), stored as f32
 
 
-def fold_program(code):
+def fold_program(code, color_is_one=True):
     """Constant-fold a postfix program on the host with numpy f32 arithmetic in exactly the
     op order of the device VM (IEEE, no contraction => same bits as evaluating per pixel).
-    `Input('color')` is the constant (1, 1, 1) on the raster path (triangle.py:48)."""
+    `Input('color')` is the constant (1, 1, 1) on the triangle path (triangle.py:48); particles carry
+    a per-particle colour (particle.py:159), so there it stays a runtime input."""
     stack = []  # items: ('c', f32[3]) constant | ('d', [instr, ...]) dynamic sub-program
 
     def code_of(item):
@@ -324,7 +325,7 @@ def fold_program(code):
         if op == _lib.OP_CONST:
             stack.append(('c', np.asarray(c, dtype=_F)))
         elif op == _lib.OP_INPUT:
-            if arg == 1:
+            if arg == 1 and color_is_one:
                 stack.append(('c', np.ones(3, dtype=_F)))
             else:
                 stack.append(('d', [ins]))
@@ -465,21 +466,21 @@ def param_signature(material):
     return tuple(p._value.tobytes() for p in params)
 
 
-def compile_material(material, fold=True):
+def compile_material(material, fold=True, color_is_one=True):
     """flatten -> constant-fold -> hoist.  -> (brdf, ambient, emission, prologue, textures)"""
     brdf, amb, emi, textures = flatten_material(material)
     pro = []
     if fold:
-        brdf, amb, emi = fold_program(brdf), fold_program(amb), fold_program(emi)
+        brdf, amb, emi = (fold_program(c, color_is_one) for c in (brdf, amb, emi))
         brdf, amb, emi, pro = hoist_programs(brdf, amb, emi)
     if len(brdf) + len(amb) + len(emi) + len(pro) > _lib.TINA_MAX_INSTR:
         raise NotImplementedError('material program too long')
     return brdf, amb, emi, pro, textures
 
 
-def material_struct(material, device, fold=True):
+def material_struct(material, device, fold=True, color_is_one=True):
     """Build the TinaMaterial POD; returns (struct, keepalive list of device tensors)."""
-    brdf, amb, emi, pro, textures = compile_material(material, fold)
+    brdf, amb, emi, pro, textures = compile_material(material, fold, color_is_one)
     m = _lib.TinaMaterial()
     m.n_brdf, m.n_ambient, m.n_emission, m.ntex = len(brdf), len(amb), len(emi), len(textures)
     m.n_prologue = len(pro)

@@ -84,8 +84,14 @@ class Scene:
                     opts = {k: v for k, v in self.options.items() if k in ('maxfaces', 'smoothing', 'texturing', 'culling', 'clipping')}
                     self.triangle_raster = TriangleRaster(self.engine, **opts)
                 raster = self.triangle_raster
-            elif hasattr(object, 'get_nfaces') or hasattr(object, 'get_npars') or hasattr(object, 'sample_volume'):
-                raise NotImplementedError('wireframe / particle / volume rasterisers are outside the B200 triangle path')
+            elif hasattr(object, 'get_npars'):  # raster.py:133-136
+                if not hasattr(self, 'particle_raster'):
+                    from .particle import ParticleRaster
+                    opts = {k: v for k, v in self.options.items() if k in ('maxpars', 'coloring', 'clipping')}
+                    self.particle_raster = ParticleRaster(self.engine, **opts)
+                raster = self.particle_raster
+            elif hasattr(object, 'get_nfaces') or hasattr(object, 'sample_volume'):
+                raise NotImplementedError('wireframe / volume rasterisers are outside the B200 raster path')
             else:
                 raise ValueError(f'cannot determine raster type of object: {object}')
         self._ensure_material_shader(material)
@@ -117,7 +123,7 @@ class Scene:
             shader = self.shaders[id(info.material)]
             info.raster.set_object(obj)
             info.raster.render_occup()
-            if isinstance(info.raster, TriangleRaster):
+            if isinstance(info.raster, TriangleRaster) or hasattr(info.raster, 'set_particles'):
                 info.raster.render_color(shader, fill_bg=bg if i == 0 else None, tonemap=fuse_tm)
             else:
                 if i == 0:

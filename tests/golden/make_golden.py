@@ -213,6 +213,60 @@ def case_gbuffers():
     np.savez_compressed(path, **d)
 
 
+def case_particles():
+    """ParticleRaster (core/particle.py) sharing depth with a triangle mesh: SimpleParticles with radii and
+    colours (Classic material, Input('color') = particle colour), a transformed copy, then monkey.obj."""
+    rng = np.random.default_rng(5)
+    scene = tina.Scene((60, 48))
+    n = 40
+    pos = (rng.random((n, 3)) * 2 - 1).astype(np.float32) * np.float32([1.0, 0.8, 0.6])
+    rad = (rng.random(n) * 0.12 + 0.03).astype(np.float32)
+    col = (rng.random((n, 3)) * 0.8 + 0.2).astype(np.float32)
+    pars = tina.SimpleParticles(maxpars=64)
+    pars.set_particles(pos)
+    pars.set_particle_radii(rad)
+    pars.set_particle_colors(col)
+    scene.add_object(pars, tina.Classic())
+    pars2 = tina.SimpleParticles(maxpars=64, radius=0.05)
+    pars2.set_particles(pos[:12] * np.float32(0.5))
+    moved = tina.ParsTransform(pars2)
+    trans = tina.translate([0.3, 0.2, 0.8]) @ tina.eularXYZ([0.2, 0.5, 0.1])
+    moved.set_transform(trans, 1.7)
+    scene.add_object(moved, tina.Diffuse())
+    scene.add_object(tina.MeshModel(os.path.join(REF, 'assets/monkey.obj')), tina.Diffuse(color=[0.3, 0.5, 0.9]))
+    camera(scene, 60 / 48, back=(0.4, 0.3, 3.0))
+    # replay Scene.render by hand (render_and_dump is triangle specific)
+    eng = scene.engine
+    scene.image.fill(scene.bgcolor)
+    eng.clear_depth()
+    out = {'res': np.array(scene.res.entries, dtype=np.int32), 'W2V': eng.W2V.to_numpy().astype(np.float32),
+           'V2W': eng.V2W.to_numpy().astype(np.float32), 'bias': eng.bias.to_numpy().astype(np.float32),
+           'pos': pos, 'rad': rad, 'col': col, 'trans': trans}
+    L = scene.lighting
+    nl = int(L.nlights[None])
+    out['light_dirs'] = L.light_dirs.to_numpy()[:nl].astype(np.float32)
+    out['light_colors'] = L.light_colors.to_numpy()[:nl].astype(np.float32)
+    out['ambient'] = L.ambient_color.to_numpy().astype(np.float32)
+    for k, (obj, oinfo) in enumerate(scene.objects.items()):
+        r = oinfo.raster
+        r.set_object(obj)
+        r.render_occup()
+        r.render_color(scene.shaders[oinfo.material])
+        out[f'occup{k}'] = r.occup.to_numpy().astype(np.int32)
+        if hasattr(r, 'npars'):
+            m = int(r.npars[None])
+            out[f'pverts{k}'] = r.verts.to_numpy()[:m].astype(np.float32)
+            out[f'psizes{k}'] = r.sizes.to_numpy()[:m].astype(np.float32)
+            out[f'pcolors{k}'] = r.colors.to_numpy()[:m].astype(np.float32)
+        else:
+            out[f'verts{k}'] = r.verts.to_numpy()[:int(r.nfaces[None])].astype(np.float32)
+        out[f'depth_after{k}'] = eng.depth.to_numpy().astype(np.int32)
+        out[f'image_after{k}'] = scene.image.to_numpy().astype(np.float32)
+    path = os.path.join(HERE, 'particles_and_mesh.npz')
+    np.savez_compressed(path, **out)
+    print('particles_and_mesh:', [int((out[f'occup{k}'] >= 0).sum()) for k in range(3)], os.path.getsize(path), 'B')
+
+
 if __name__ == '__main__':
     np.seterr(all='ignore')
     case_monkey()
@@ -222,3 +276,4 @@ if __name__ == '__main__':
     case_multi_object()
     case_lights_materials()
     case_gbuffers()
+    case_particles()

@@ -16,7 +16,8 @@ import pytest
 import scenes
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
-CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, '*.npz')))
+CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, '*.npz'))
+               if not os.path.basename(p).startswith('particles'))
 COLOR_TOL = 2e-6
 
 
@@ -164,3 +165,36 @@ def test_accumulator_formula_matches_reference_source():
         inv = np.float32(1) / np.float32(k)
         mine = mine * (np.float32(1) - inv) + frame * inv
         assert np.array_equal(A.img.to_numpy(), mine)
+
+
+def _pars_scene(tina, g):
+    """(kind, arrays, material) per object of tests/golden/particles_and_mesh.npz"""
+    return [('pars', (g['pverts0'], g['psizes0'], g['pcolors0']), tina.Classic()),
+            ('pars', (g['pverts1'], g['psizes1'], g['pcolors1']), tina.Diffuse()),
+            ('mesh', (g['verts2'],), tina.Diffuse(color=[0.3, 0.5, 0.9]))]
+
+
+def test_oracle_particles_match_reference_sources(tina, O):
+    """core/particle.py + pars/{simple,trans}.py under the shim, interleaved with a triangle mesh on one depth
+    buffer: ids + depth bit-exact after every object, colours <= 2e-6."""
+    g = np.load(os.path.join(GOLDEN, 'particles_and_mesh.npz'))
+    W, H = (int(v) for v in g['res'])
+    lighting = _lighting(tina, g)
+    # ParsTransform (pars/trans.py:22-31): positions through mapply_pos, radii scaled
+    v1, _ = O.transform((g['pos'][:12] * np.float32(0.5)).reshape(-1, 1, 3), None, g['trans'])
+    assert np.array_equal(v1.reshape(-1, 3), g['pverts1'])
+    assert np.array_equal(np.float32(1.7) * np.full(12, np.float32(0.05)), g['psizes1'])
+    assert np.array_equal(g['pverts0'], g['pos']) and np.array_equal(g['psizes0'], g['rad'])
+    depth = O.clear_depth(W, H)
+    image = np.zeros((W, H, 3), np.float32)
+    for k, (kind, arr, mat) in enumerate(_pars_scene(tina, g)):
+        if kind == 'pars':
+            occup, depth = O.pars_occup(arr[0], arr[1], g['W2V'], g['V2W'], W, H, True, g['bias'], depth)
+            O.pars_color(arr[0], arr[1], arr[2], occup, g['W2V'], g['V2W'], W, H, mat, lighting, image, g['bias'])
+        else:
+            occup, depth, _, _ = O.render_occup(arr[0], g['W2V'], W, H, O.CULLING | O.CLIPPING, g['bias'], depth)
+            O.render_color(arr[0], None, None, occup, g['W2V'], g['V2W'], W, H, O.CULLING | O.CLIPPING, mat, lighting, image, g['bias'])
+        assert np.array_equal(occup, g[f'occup{k}']), k
+        assert np.array_equal(depth, g[f'depth_after{k}']), k
+        assert np.abs(image - g[f'image_after{k}']).max() <= COLOR_TOL, k
+    assert (g['occup0'] >= 0).sum() > 100 and (g['occup2'] >= 0).sum() > 100
