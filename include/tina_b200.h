@@ -222,6 +222,18 @@ int tina_pars_render_color(TinaPars *r, const TinaMaterial *mat_host, const Tina
                            uint32_t flags, const float *bg_host, void *stream); /* particle.py:129-161 */
 int tina_pars_occup(TinaPars *r, int32_t *occup, void *stream);
 
+/* ---- WireframeRaster (core/wireframe.py:4-95): depth-tested DDA lines on the same Engine ---- */
+typedef struct TinaWire TinaWire;
+/* flags: 2 = clipping (wireframe.py:7); linecolor_host: 3 floats or NULL for the default (.9, .6, 0) */
+int tina_wire_create(TinaWire **out, TinaEngine *e, int64_t maxwires, uint32_t flags, const float *linecolor_host);
+int tina_wire_destroy(TinaWire *w);
+int tina_wire_set_color(TinaWire *w, const float *linecolor_host);
+/* set_object (wireframe.py:32-38): npoly = 0: verts [N,2,3] borrowed; npoly > 0: polygon faces [N/npoly, npoly, 3]
+ * turned into their N edges like MeshToWire (mesh/wire.py:19-27) */
+int tina_wire_set(TinaWire *w, const float *verts, int64_t nwires, int npoly, void *stream);
+/* wireframe.py:70-95 (render_occup is a no-op there): depth test + Shader.blend_color(1, linecolor) into each image */
+int tina_wire_render_color(TinaWire *w, float *const *images_host, int nimages, void *stream);
+
 /* ---- frame glue (scene/raster.py:176,202-203) -------------------------------- */
 int tina_image_fill(float *image, int64_t npixels, const float *rgb_host, void *stream);
 int tina_image_tonemap(float *image, int64_t nfloats, void *stream);

@@ -147,6 +147,22 @@ def render_gbuffer(kind, verts, norms, coors, occup, depth, W2V, V2W, W, H, flag
     return out
 
 
+def wire_render(verts, W2V, W, H, depth, image, color=(.9, .6, 0), clipping=False, bias=(0.5, 0.5)):
+    """core/wireframe.py:70-95 on wires [N,2,3]; -> (depth copy updated, image modified in place)"""
+    verts = _f(verts).reshape(-1, 6)
+    depth = np.ascontiguousarray(depth, dtype=np.int32).copy()
+    lib().orc_wire_render(_p(verts), C.c_int64(len(verts)), _p(_f(W2V).reshape(16)), _p(_f(bias)), W, H,
+                          C.c_uint32(2 if clipping else 0), _p(_f(color)), _p(depth), _p(image))
+    return depth, image
+
+
+def mesh_to_wires(face_verts):
+    """mesh/wire.py:19-27 on expanded faces [N,3,3] -> [3N,2,3]"""
+    fv = _f(face_verts)
+    idx = np.arange(len(fv) * 3)
+    return np.ascontiguousarray(np.stack([fv[idx // 3, idx % 3], fv[idx // 3, (idx + 1) % 3]], axis=1))
+
+
 def tonemap(image):
     out = np.ascontiguousarray(image, dtype=np.float32).copy()
     lib().orc_tonemap(_p(out), C.c_int64(out.size))

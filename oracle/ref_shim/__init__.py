@@ -235,19 +235,23 @@ def _scalar(x):
     return x[()]
 
 
-class IntRef(builtins.int):
+class TiInt(builtins.int):
+    """A runtime i32 value: Taichi's `/` on ints is a true division in default_fp (f32), not Python's f64
+    (e.g. `i / siz` in wireframe.py:66, `1 / count` in accumator.py:18)."""
+
+    def __truediv__(self, o):
+        return F32(builtins.int(self)) / (F32(o) if isinstance(o, (builtins.int, np.integer)) else o)
+
+    def __rtruediv__(self, o):
+        return (F32(o) if isinstance(o, (builtins.int, np.integer)) else o) / F32(builtins.int(self))
+
+
+class IntRef(TiInt):
     """Value of an int scalar field element that remembers where it lives (lvalue for ti.atomic_*)."""
     def __new__(cls, value, field, idx):
         o = builtins.int.__new__(cls, value)
         o.field, o.idx = field, idx
         return o
-
-    # a runtime i32 value: Taichi's `/` is a true division in default_fp (f32), not Python's f64
-    def __truediv__(self, o):
-        return F32(builtins.int(self)) / (F32(o) if isinstance(o, (builtins.int, IntRef)) else o)
-
-    def __rtruediv__(self, o):
-        return (F32(o) if isinstance(o, (builtins.int, IntRef)) else o) / F32(builtins.int(self))
 
 
 def _dtype(dt):
@@ -352,7 +356,7 @@ def _to_int(x):
     if isinstance(x, Matrix):
         return Matrix(_f2i(x.a), _raw=True)
     if isinstance(x, np.floating):
-        return I32(_f2i(x))
+        return TiInt(_f2i(x))
     return builtins.int(x)
 
 
@@ -477,7 +481,7 @@ def make_transformations():
 
 NEEDED = ['common', 'advans', 'util.matrix', 'matr.nodes', 'matr.material', 'core.engine', 'core.lighting',
           'core.shader', 'core.triangle', 'mesh.base', 'mesh.simple', 'mesh.model', 'mesh.grid', 'mesh.trans',
-          'mesh.cull', 'mesh.norm', 'postp.tonemap', 'assimp.obj', 'assimp.gltf', 'core.particle', 'pars.base',
+          'mesh.cull', 'mesh.norm', 'postp.tonemap', 'assimp.obj', 'assimp.gltf', 'core.particle', 'core.wireframe', 'mesh.wire', 'pars.base',
           'pars.simple', 'pars.trans', 'scene.raster']
 
 

@@ -625,6 +625,60 @@ void orc_pars_color(const float *verts, const float *sizes, const float *colors,
         }
 }
 
+/* ---- WireframeRaster (core/wireframe.py:49-95), serial order; flags: 2 = clipping.  verts [N][2][3].
+ * On a depth win the pixel of `image` becomes img * (1 - 1) + color * 1 (Shader.blend_color, shader.py:133-135). */
+void orc_wire_render(const float *verts, int64_t nwires, const float *W2V, const float *bias, int W, int H, uint32_t flags,
+                     const float *color, int32_t *depth, float *image) {
+    float res[2] = {(float)W, (float)H};
+    for (int64_t f = 0; f < nwires; f++) {
+        const float *Al = verts + f * 6, *Bl = Al + 3;
+        float Av[3], Bv[3], t[3], rwa, rwb;
+        mapply(W2V, Al, 1.0f, t, &rwa);
+        for (int k = 0; k < 3; k++) Av[k] = t[k] / rwa;
+        mapply(W2V, Bl, 1.0f, t, &rwb);
+        for (int k = 0; k < 3; k++) Bv[k] = t[k] / rwb;
+        if (flags & 2u) {
+            int ina = 1, inb = 1;
+            for (int k = 0; k < 3; k++) {
+                ina &= (-1.0f <= Av[k]) && (Av[k] <= 1.0f);
+                inb &= (-1.0f <= Bv[k]) && (Bv[k] <= 1.0f);
+            }
+            if (!ina && !inb) continue;
+        }
+        float a[2], b[2];
+        for (int k = 0; k < 2; k++) a[k] = (Av[k] * 0.5f + 0.5f) * res[k], b[k] = (Bv[k] * 0.5f + 0.5f) * res[k];
+        float wsc[2] = {1.0f / rwa, 1.0f / rwb};
+        float dlt[2] = {b[0] - a[0], b[1] - a[1]}, adlt[2] = {fabsf(dlt[0]), fabsf(dlt[1])}, k[2] = {1.0f, 1.0f};
+        int32_t siz;
+        if (adlt[0] >= adlt[1]) {
+            k[0] = dlt[0] >= 0 ? 1.0f : -1.0f;
+            k[1] = k[0] * dlt[1] / dlt[0];
+            siz = f2i(adlt[0]);
+        } else {
+            k[1] = dlt[1] >= 0 ? 1.0f : -1.0f;
+            k[0] = k[1] * dlt[0] / dlt[1];
+            siz = f2i(adlt[1]);
+        }
+        for (int64_t i = 0; i < (int64_t)siz + 1; i++) {
+            float fi = (float)i;
+            float pos[2] = {(a[0] + k[0] * fi) + bias[0], (a[1] + k[1] * fi) + bias[1]};
+            int32_t Px = ifloor_(pos[0]), Py = ifloor_(pos[1]);
+            if (!(0 <= Px && Px < W && 0 <= Py && Py < H)) continue;
+            float cor = fi / (float)siz;
+            float wei[2] = {(1.0f - cor) * wsc[0], cor * wsc[1]};
+            float sum = wei[0] + wei[1];
+            wei[0] = wei[0] / sum, wei[1] = wei[1] / sum;
+            int32_t d = f2i((wei[0] * Av[2] + wei[1] * Bv[2]) * MAXDEPTH_F);
+            int64_t P = (int64_t)Px * H + Py;
+            if (depth[P] > d) {
+                depth[P] = d;
+                if (image)
+                    for (int c = 0; c < 3; c++) image[P * 3 + c] = image[P * 3 + c] * 0.0f + color[c] * 1.0f;
+            }
+        }
+    }
+}
+
 /* ---- mesh providers feeding set_object ------------------------------------------ */
 
 /* mesh/grid.py:26-35 MeshGrid.pre_compute; pos, nrm: [nx][ny][3] */

@@ -18,6 +18,7 @@ from .mesh import (MAX, SimpleMesh, MeshModel, MeshGrid, MeshTransform, MeshFlip
 from .engine import Engine
 from .triangle import TriangleRaster
 from .particle import ParticleRaster, SimpleParticles, ParsTransform
+from .wireframe import WireframeRaster, MeshToWire
 from .scene import Scene
 from .control import Control, RotationStep
 from .field import Field

@@ -77,6 +77,11 @@ SIGNATURES = {
     'tina_pars_render_occup': (_i, [_vp, _vp]),
     'tina_pars_render_color': (_i, [_vp, C.POINTER(TinaMaterial), C.POINTER(TinaLighting), _vp, _u32, _fp, _vp]),
     'tina_pars_occup': (_i, [_vp, _vp, _vp]),
+    'tina_wire_create': (_i, [C.POINTER(_vp), _vp, _i64, _u32, _fp]),
+    'tina_wire_destroy': (_i, [_vp]),
+    'tina_wire_set_color': (_i, [_vp, _fp]),
+    'tina_wire_set': (_i, [_vp, _vp, _i64, _i, _vp]),
+    'tina_wire_render_color': (_i, [_vp, C.POINTER(_vp), _i, _vp]),
     'tina_image_fill': (_i, [_vp, _i64, _fp, _vp]),
     'tina_image_tonemap': (_i, [_vp, _i64, _vp]),
     'tina_image_accumulate': (_i, [_vp, _vp, _i64, _i, _vp]),

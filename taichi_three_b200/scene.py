@@ -79,7 +79,13 @@ class Scene:
         if material is None:
             material = self.default_material
         if raster is None:
-            if hasattr(object, 'get_nfaces') and not (hasattr(object, 'get_npolygon') and object.get_npolygon() == 2):
+            if hasattr(object, 'get_nfaces') and hasattr(object, 'get_npolygon') and object.get_npolygon() == 2:
+                if not hasattr(self, 'wireframe_raster'):  # raster.py:124-128
+                    from .wireframe import WireframeRaster
+                    opts = {k: v for k, v in self.options.items() if k in ('maxwires', 'linewidth', 'linecolor', 'clipping')}
+                    self.wireframe_raster = WireframeRaster(self.engine, **opts)
+                raster = self.wireframe_raster
+            elif hasattr(object, 'get_nfaces'):
                 if not hasattr(self, 'triangle_raster'):
                     opts = {k: v for k, v in self.options.items() if k in ('maxfaces', 'smoothing', 'texturing', 'culling', 'clipping')}
                     self.triangle_raster = TriangleRaster(self.engine, **opts)
@@ -90,8 +96,8 @@ class Scene:
                     opts = {k: v for k, v in self.options.items() if k in ('maxpars', 'coloring', 'clipping')}
                     self.particle_raster = ParticleRaster(self.engine, **opts)
                 raster = self.particle_raster
-            elif hasattr(object, 'get_nfaces') or hasattr(object, 'sample_volume'):
-                raise NotImplementedError('wireframe / volume rasterisers are outside the B200 raster path')
+            elif hasattr(object, 'sample_volume'):
+                raise NotImplementedError('the volume rasteriser is outside the B200 raster path')
             else:
                 raise ValueError(f'cannot determine raster type of object: {object}')
         self._ensure_material_shader(material)

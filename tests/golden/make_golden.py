@@ -267,6 +267,42 @@ def case_particles():
     print('particles_and_mesh:', [int((out[f'occup{k}'] >= 0).sum()) for k in range(3)], os.path.getsize(path), 'B')
 
 
+def case_wireframe():
+    """WireframeRaster + MeshToWire (core/wireframe.py, mesh/wire.py) over a solid mesh: depth-tested lines."""
+    scene = tina.Scene((64, 56), tonemap=False)
+    obj = tina.readobj(os.path.join(REF, 'assets/monkey.obj'))
+    solid = tina.MeshTransform(tina.MeshModel(obj), tina.scale(0.97))
+    scene.add_object(solid, tina.Diffuse(color=[0.2, 0.3, 0.4]))
+    wire = tina.MeshToWire(tina.MeshModel(obj))
+    scene.add_object(wire)
+    camera(scene, 64 / 56, back=(0.6, 0.5, 2.7))
+    eng = scene.engine
+    scene.image.fill(scene.bgcolor)
+    eng.clear_depth()
+    out = {'res': np.array(scene.res.entries, dtype=np.int32), 'W2V': eng.W2V.to_numpy().astype(np.float32),
+           'V2W': eng.V2W.to_numpy().astype(np.float32), 'bias': eng.bias.to_numpy().astype(np.float32)}
+    L = scene.lighting
+    nl = int(L.nlights[None])
+    out['light_dirs'] = L.light_dirs.to_numpy()[:nl].astype(np.float32)
+    out['light_colors'] = L.light_colors.to_numpy()[:nl].astype(np.float32)
+    out['ambient'] = L.ambient_color.to_numpy().astype(np.float32)
+    for k, (o, oinfo) in enumerate(scene.objects.items()):
+        r = oinfo.raster
+        r.set_object(o)
+        r.render_occup()
+        r.render_color(scene.shaders[oinfo.material])
+        if k == 0:
+            out['verts0'] = r.verts.to_numpy()[:int(r.nfaces[None])].astype(np.float32)
+        else:
+            out['wires1'] = r.verts.to_numpy()[:int(r.nwires[None])].astype(np.float32)
+        out[f'depth_after{k}'] = eng.depth.to_numpy().astype(np.int32)
+        out[f'image_after{k}'] = scene.image.to_numpy().astype(np.float32)
+    path = os.path.join(HERE, 'particles_wireframe_over_mesh.npz')
+    np.savez_compressed(path, **out)
+    changed = int((out['depth_after1'] != out['depth_after0']).sum())
+    print('wireframe:', out['wires1'].shape, 'wire pixels', changed, os.path.getsize(path), 'B')
+
+
 if __name__ == '__main__':
     np.seterr(all='ignore')
     case_monkey()
@@ -277,3 +313,4 @@ if __name__ == '__main__':
     case_lights_materials()
     case_gbuffers()
     case_particles()
+    case_wireframe()

@@ -198,3 +198,22 @@ def test_oracle_particles_match_reference_sources(tina, O):
         assert np.array_equal(depth, g[f'depth_after{k}']), k
         assert np.abs(image - g[f'image_after{k}']).max() <= COLOR_TOL, k
     assert (g['occup0'] >= 0).sum() > 100 and (g['occup2'] >= 0).sum() > 100
+
+
+def test_oracle_wireframe_matches_reference_sources(tina, O):
+    """core/wireframe.py + mesh/wire.py under the shim over a solid mesh: depth bit-exact, image identical."""
+    g = np.load(os.path.join(GOLDEN, 'particles_wireframe_over_mesh.npz'))
+    W, H = (int(v) for v in g['res'])
+    lighting = _lighting(tina, g)
+    flags = O.CULLING | O.CLIPPING
+    occup, depth, _, _ = O.render_occup(g['verts0'], g['W2V'], W, H, flags, g['bias'])
+    image = np.zeros((W, H, 3), np.float32)
+    O.render_color(g['verts0'], None, None, occup, g['W2V'], g['V2W'], W, H, flags, tina.Diffuse(color=[0.2, 0.3, 0.4]), lighting, image, g['bias'])
+    assert np.array_equal(depth, g['depth_after0']) and np.abs(image - g['image_after0']).max() <= COLOR_TOL
+    v, _, _ = O.indexed(scenes.load_monkey())
+    wires = O.mesh_to_wires(v)
+    assert np.array_equal(wires, g['wires1'])  # MeshToWire
+    depth, image = O.wire_render(wires, g['W2V'], W, H, depth, image, bias=g['bias'])
+    assert np.array_equal(depth, g['depth_after1'])
+    assert np.abs(image - g['image_after1']).max() <= COLOR_TOL
+    assert (g['depth_after1'] != g['depth_after0']).sum() > 500

@@ -642,3 +642,44 @@ def test_particle_raster_matches_reference_golden(tina):
     img = tina.Field(torch.zeros((W, H, 3), device='cuda'))
     pr.render_color(tina.Shader(img, _lighting(tina, g), tina.Classic()))
     assert np.abs(img.to_numpy() - g['image_after0']).max() <= COLOR_TOL
+
+
+def test_wireframe_raster_matches_reference_golden(tina, O):
+    """§8f row 3: WireframeRaster + MeshToWire through tina.Scene over a solid mesh, against the golden produced
+    by the reference's own sources; plus long / off-screen / degenerate lines against the oracle."""
+    import os
+    import torch
+    from test_golden import GOLDEN
+    g = np.load(os.path.join(GOLDEN, 'particles_wireframe_over_mesh.npz'))
+    W, H = (int(v) for v in g['res'])
+    obj = scenes.load_monkey()
+    scene = tina.Scene((W, H), tonemap=False)
+    scene.add_object(tina.MeshTransform(tina.MeshModel(obj), tina.scale(0.97)), tina.Diffuse(color=[0.2, 0.3, 0.4]))
+    scene.add_object(tina.MeshToWire(tina.MeshModel(obj)))
+    scene.engine.W2V[None], scene.engine.V2W[None], scene.engine.bias[None] = g['W2V'], g['V2W'], g['bias']
+    scene.render()
+    torch.cuda.synchronize()
+    assert np.array_equal(scene.engine.depth.to_numpy(), g['depth_after1'])
+    assert np.abs(scene.img.to_numpy() - g['image_after1']).max() <= COLOR_TOL
+    # stress: long lines crossing the screen, lines far outside, zero-length, behind the camera, clipping on/off
+    rng = np.random.default_rng(9)
+    wires = (rng.random((3000, 2, 3)).astype(np.float32) * 2 - 1) * np.float32([2.5, 2.5, 1.5])
+    wires[:40] *= 40  # huge
+    wires[40:60, 1] = wires[40:60, 0]  # zero length
+    wires[60:80, :, 2] += 4  # behind the camera
+    view, proj = scenes.default_camera(W / H)
+    for clipping in (False, True):
+        engine = tina.Engine((W, H))
+        engine.set_camera(view, proj)
+        wr = tina.WireframeRaster(engine, clipping=clipping, linecolor=(0.1, 0.7, 0.3))
+        wr.set_wire_verts(wires)
+        img = tina.Field(torch.zeros((W, H, 3), device='cuda'))
+        engine.clear_depth()
+        lighting = tina.Lighting()
+        wr.render_color(tina.Shader(img, lighting, tina.Diffuse()))
+        torch.cuda.synchronize()
+        with np.errstate(all='ignore'):
+            d, im = O.wire_render(wires, (proj @ view).astype(np.float32), W, H, O.clear_depth(W, H), np.zeros((W, H, 3), np.float32),
+                                  color=(0.1, 0.7, 0.3), clipping=clipping)
+        assert np.array_equal(engine.depth.to_numpy(), d), clipping
+        assert np.array_equal(img.to_numpy(), im), clipping
