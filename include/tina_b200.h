@@ -52,9 +52,6 @@ typedef struct TinaRaster TinaRaster;
 #define TINA_COLOR_TONEMAP 1u /* fuse aces_tonemap (advans.py:32-35) into the store            */
 #define TINA_COLOR_FILL_BG 2u /* also write `bg` to pixels this object does not own (raster.py:176) */
 
-/* rasteriser strategy knobs (tina_raster_set_tuning): all settings give identical bits */
-#define TINA_TUNE_DEFAULT (-1)
-
 #define TINA_MAX_LIGHTS 16 /* lighting.py:26 */
 #define TINA_MAX_INSTR 96
 #define TINA_MAX_TEX 4
