@@ -35,6 +35,23 @@ sys.path.insert(0, os.path.join(ROOT, 'tests'))
 import numpy as np  # noqa: E402
 
 
+def ncu_traffic(kernel_file='r1_v6_k_raster_faces_indexed_ncu.txt'):
+    """DRAM bytes (read + write) per launch of the dominant kernel from the committed `ncu --set full` summary
+    under profiles/ (tools/ncu_summary.py output).  None if the file is missing."""
+    p = os.path.join(ROOT, 'profiles', kernel_file)
+    try:
+        tot, seen = 0.0, 0
+        for line in open(p):
+            f = line.split()
+            if len(f) >= 3 and f[0] in ('dram__bytes_read.sum', 'dram__bytes_write.sum') and seen < 2:
+                scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}[f[2]]
+                tot += float(f[1]) * scale
+                seen += 1
+        return tot if seen == 2 else None
+    except Exception:
+        return None
+
+
 def load_peaks():
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(p):
@@ -391,7 +408,9 @@ def run_ours(args):
             'step_ms_min_median_max': [float(step_ms.min()), float(np.median(step_ms)), float(step_ms.max())],
             'kernel_ms': kmean,
             'roofline': {'bound': 'hbm', 'kernel': 'k_raster_faces', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                         'frac': achieved / peak, 'traffic': None, 'alg_bytes': k1_bytes, 'peak_source': peak_src},
+                         'frac': achieved / peak, 'traffic': ncu_traffic() if wl == 'c2' else None,
+                         'traffic_source': 'profiles/r1_v6_k_raster_faces_indexed_ncu.txt (ncu --set full, dram read+write per launch)',
+                         'alg_bytes': k1_bytes, 'peak_source': peak_src},
             'cpu_baseline': cpu,
             'e2e': {'value': e2e_value, 'unit': 'Mtris/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'ms_per_step': e2e_s * 1e3, 'steps': Ke, 'image_checksum': checksum,

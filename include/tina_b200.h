@@ -234,6 +234,15 @@ int tina_wire_render_color(TinaWire *w, float *const *images_host, int nimages, 
 /* ---- frame glue (scene/raster.py:176,202-203) -------------------------------- */
 int tina_image_fill(float *image, int64_t npixels, const float *rgb_host, void *stream);
 int tina_image_tonemap(float *image, int64_t nfloats, void *stream);
+/* FXAA (postp/fxaa.py:28-68) in place on image [W,H,3]; scratch_lumi [W*H], scratch_copy [W*H*3] floats.
+ * Reference defaults: abs_thresh 0.0625, rel_thresh 0.063, factor 1.  Out-of-image taps read 0. */
+int tina_image_fxaa(float *image, int W, int H, float *scratch_lumi, float *scratch_copy, float abs_thresh,
+                    float rel_thresh, float factor, void *stream);
+/* Blooming (postp/blooming.py:45-68) in place; scratch_a/b: [(W/2)*(H/2)*3] floats; gwei: device [radius+1]
+ * normalised Gaussian weights (blooming.py:26-37).  Reference defaults: thresh 1, scale 0.25, factor 1,
+ * radius min(W,H)/16, sigma 1. */
+int tina_image_bloom(float *image, int W, int H, float *scratch_a, float *scratch_b, const float *gwei, int radius,
+                     float thresh, float scale, float factor, void *stream);
 /* TAA accumulation, util/accumator.py:16-23: acc = acc * (1 - 1/count) + src * (1/count), count >= 1 */
 int tina_image_accumulate(float *acc, const float *src, int64_t nfloats, int count, void *stream);
 

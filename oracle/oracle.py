@@ -163,6 +163,19 @@ def mesh_to_wires(face_verts):
     return np.ascontiguousarray(np.stack([fv[idx // 3, idx % 3], fv[idx // 3, (idx + 1) % 3]], axis=1))
 
 
+def fxaa(image, abs_thresh=0.0625, rel_thresh=0.063, factor=1.0):
+    out = np.ascontiguousarray(image, dtype=np.float32).copy()
+    lib().orc_fxaa(_p(out), out.shape[0], out.shape[1], C.c_float(abs_thresh), C.c_float(rel_thresh), C.c_float(factor))
+    return out
+
+
+def bloom(image, gwei, thresh=1.0, scale=0.25, factor=1.0):
+    out = np.ascontiguousarray(image, dtype=np.float32).copy()
+    g = _f(gwei)
+    lib().orc_bloom(_p(out), out.shape[0], out.shape[1], _p(g), len(g) - 1, C.c_float(thresh), C.c_float(scale), C.c_float(factor))
+    return out
+
+
 def tonemap(image):
     out = np.ascontiguousarray(image, dtype=np.float32).copy()
     lib().orc_tonemap(_p(out), C.c_int64(out.size))

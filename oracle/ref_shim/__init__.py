@@ -481,7 +481,7 @@ def make_transformations():
 
 NEEDED = ['common', 'advans', 'util.matrix', 'matr.nodes', 'matr.material', 'core.engine', 'core.lighting',
           'core.shader', 'core.triangle', 'mesh.base', 'mesh.simple', 'mesh.model', 'mesh.grid', 'mesh.trans',
-          'mesh.cull', 'mesh.norm', 'postp.tonemap', 'assimp.obj', 'assimp.gltf', 'core.particle', 'core.wireframe', 'mesh.wire', 'pars.base',
+          'mesh.cull', 'mesh.norm', 'postp.tonemap', 'postp.fxaa', 'postp.blooming', 'assimp.obj', 'assimp.gltf', 'core.particle', 'core.wireframe', 'mesh.wire', 'pars.base',
           'pars.simple', 'pars.trans', 'scene.raster']
 
 

@@ -679,6 +679,103 @@ void orc_wire_render(const float *verts, int64_t nwires, const float *W2V, const
     }
 }
 
+/* ---- post effects (postp/fxaa.py:28-68, postp/blooming.py:45-68); x-major [W][H]; out-of-shape reads = 0 ---- */
+static float ld2(const float *f, int W, int H, int x, int y) { return (x < 0 || y < 0 || x >= W || y >= H) ? 0.0f : f[(int64_t)x * H + y]; }
+static void ld2v(const float *f, int W, int H, int x, int y, float *o) {
+    if (x < 0 || y < 0 || x >= W || y >= H) {
+        o[0] = o[1] = o[2] = 0.0f;
+        return;
+    }
+    memcpy(o, f + ((int64_t)x * H + y) * 3, 3 * sizeof(float));
+}
+static void bilerp3(const float *f, int W, int H, float px, float py, float *o) { /* common.py:140-149 */
+    int32_t I0 = ifloor_(px), I1 = ifloor_(py);
+    float x0 = px - (float)I0, x1 = py - (float)I1, y0 = 1.0f - x0, y1 = 1.0f - x1, a[3], b[3], c[3], d[3];
+    ld2v(f, W, H, I0 + 1, I1 + 1, a), ld2v(f, W, H, I0 + 1, I1, b), ld2v(f, W, H, I0, I1, c), ld2v(f, W, H, I0, I1 + 1, d);
+    for (int k = 0; k < 3; k++) o[k] = ((a[k] * x0 * x1 + b[k] * x0 * y1) + c[k] * y0 * y1) + d[k] * y0 * x1;
+}
+static float clamp01(float x) { return fminf(1.0f, fmaxf(0.0f, x)); }
+
+void orc_fxaa(float *image, int W, int H, float abs_thresh, float rel_thresh, float factor) {
+    int64_t npix = (int64_t)W * H;
+    float *lumi = malloc(sizeof(float) * npix), *copy = malloc(sizeof(float) * npix * 3);
+    for (int64_t i = 0; i < npix; i++) {
+        lumi[i] = clamp01((0.2989f * image[i * 3] + 0.587f * image[i * 3 + 1]) + 0.114f * image[i * 3 + 2]);
+        memcpy(copy + i * 3, image + i * 3, 3 * sizeof(float));
+    }
+    for (int x = 0; x < W; x++)
+        for (int y = 0; y < H; y++) {
+            int64_t i = (int64_t)x * H + y;
+            float m = lumi[i], n = ld2(lumi, W, H, x, y + 1), e = ld2(lumi, W, H, x + 1, y), s = ld2(lumi, W, H, x, y - 1);
+            float w = ld2(lumi, W, H, x - 1, y), ne = ld2(lumi, W, H, x + 1, y + 1), nw = ld2(lumi, W, H, x - 1, y + 1);
+            float se = ld2(lumi, W, H, x + 1, y - 1), sw = ld2(lumi, W, H, x - 1, y - 1);
+            float hi = fmaxf(fmaxf(fmaxf(fmaxf(m, n), e), s), w), lo = fminf(fminf(fminf(fminf(m, n), e), s), w);
+            float c = hi - lo;
+            if (c < abs_thresh || c < rel_thresh * hi) continue;
+            float filt = 2.0f * (((n + e) + s) + w);
+            filt += ((ne + nw) + se) + sw;
+            filt = fabsf(filt / 12.0f - m);
+            filt = clamp01(filt / c);
+            float t = clamp01((filt - 0.0f) / (1.0f - 0.0f)), sm = t * t * (3.0f - 2.0f * t);
+            float blend = (sm * sm) * factor;
+            float hori = fabsf((n + s) - 2.0f * m) * 2.0f;
+            hori += fabsf((ne + se) - 2.0f * e);
+            hori += fabsf((nw + sw) - 2.0f * w);
+            float vert = fabsf((e + w) - 2.0f * m) * 2.0f;
+            vert += fabsf((ne + nw) - 2.0f * n);
+            vert += fabsf((se + sw) - 2.0f * s);
+            int is_hori = hori >= vert;
+            float plumi = is_hori ? n : e, nlumi = is_hori ? s : w;
+            if (fabsf(plumi - m) < fabsf(nlumi - m)) blend = -blend;
+            bilerp3(copy, W, H, (float)x + blend * (is_hori ? 0.0f : 1.0f), (float)y + blend * (is_hori ? 1.0f : 0.0f), image + i * 3);
+        }
+    free(lumi), free(copy);
+}
+
+static float bloom_filter(float x, float thresh, float scale, float factor) {
+    float t = fmaxf(0.0f, x - thresh);
+    t = 1.0f - 1.0f / (1.0f + scale * t);
+    return factor * t;
+}
+void orc_bloom(float *image, int W, int H, const float *gwei, int radius, float thresh, float scale, float factor) {
+    int hw = W / 2, hh = H / 2;
+    float *a = malloc(sizeof(float) * hw * hh * 3), *b = malloc(sizeof(float) * hw * hh * 3);
+    for (int x = 0; x < hw; x++)
+        for (int y = 0; y < hh; y++) {
+            float r[3] = {0, 0, 0}, c[3];
+            for (int jx = 0; jx < 2; jx++)
+                for (int jy = 0; jy < 2; jy++) {
+                    ld2v(image, W, H, x * 2 + jx, y * 2 + jy, c);
+                    for (int k = 0; k < 3; k++) r[k] += bloom_filter(c[k], thresh, scale, factor);
+                }
+            for (int k = 0; k < 3; k++) a[((int64_t)x * hh + y) * 3 + k] = r[k] / 4.0f;
+        }
+    for (int axis = 0; axis < 2; axis++) {
+        const float *src = axis ? b : a;
+        float *dst = axis ? a : b;
+        for (int x = 0; x < hw; x++)
+            for (int y = 0; y < hh; y++)
+                for (int k = 0; k < 3; k++) {
+                    float r = src[((int64_t)x * hh + y) * 3 + k] * gwei[0];
+                    for (int i = 1; i <= radius; i++) {
+                        int xa = axis ? x : (x - i > 0 ? x - i : 0), ya = axis ? (y - i > 0 ? y - i : 0) : y;
+                        int xb = axis ? x : (x + i < hw - 1 ? x + i : hw - 1), yb = axis ? (y + i < hh - 1 ? y + i : hh - 1) : y;
+                        float v = src[((int64_t)xa * hh + ya) * 3 + k];
+                        v += src[((int64_t)xb * hh + yb) * 3 + k];
+                        r += v * gwei[i];
+                    }
+                    dst[((int64_t)x * hh + y) * 3 + k] = r;
+                }
+    }
+    for (int x = 0; x < W; x++)
+        for (int y = 0; y < H; y++) {
+            float o[3];
+            bilerp3(a, hw, hh, (float)x / 2.0f, (float)y / 2.0f, o);
+            for (int k = 0; k < 3; k++) image[((int64_t)x * H + y) * 3 + k] += o[k];
+        }
+    free(a), free(b);
+}
+
 /* ---- mesh providers feeding set_object ------------------------------------------ */
 
 /* mesh/grid.py:26-35 MeshGrid.pre_compute; pos, nrm: [nx][ny][3] */

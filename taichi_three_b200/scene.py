@@ -40,7 +40,7 @@ class Accumator:
 
 
 class Scene:
-    UNSUPPORTED = ('ibl', 'ssr', 'ssao', 'fxaa', 'blooming')
+    UNSUPPORTED = ('ibl', 'ssr', 'ssao')
 
     def __init__(self, res_x=512, res_y=None, **options):
         self.engine = Engine(res_x, res_y)
@@ -61,6 +61,14 @@ class Scene:
         self.shaders = {}
         self.objects = {}
         self.pp_img = self.image
+        self.blooming = options.get('blooming', False)
+        self.fxaa = options.get('fxaa', False)
+        if self.blooming:  # raster.py:74-75
+            from .postp import Blooming
+            self.blooming = Blooming(self.res)
+        if self.fxaa:  # raster.py:82-83
+            from .postp import FXAA
+            self.fxaa = FXAA(self.res)
         if self.taa:
             self.accum = Accumator(self.res, self.engine.device)
         # raster.py:90-93
@@ -124,7 +132,7 @@ class Scene:
         bg = np.broadcast_to(np.asarray(self.bgcolor, dtype=np.float32), (3,))
         if not items:
             self.image.fill(bg)
-        fuse_tm = bool(self.tonemap) and len(items) == 1
+        fuse_tm = bool(self.tonemap) and len(items) == 1 and not self.blooming
         for i, (obj, info) in enumerate(items):
             shader = self.shaders[id(info.material)]
             info.raster.set_object(obj)
@@ -135,9 +143,13 @@ class Scene:
                 if i == 0:
                     self.image.fill(bg)
                 info.raster.render_color(shader)
+        if self.blooming:  # raster.py:200-201
+            self.blooming.apply(self.image)
         if self.tonemap and not fuse_tm:
             t = self.image.to_torch()
             _lib.check(_lib.lib().tina_image_tonemap(C.c_void_p(t.data_ptr()), t.numel(), _stream()))
+        if self.fxaa:  # raster.py:204-205
+            self.fxaa.apply(self.image)
         if self.taa:  # raster.py:206-207
             self.accum.update(self.pp_img)
 

@@ -303,6 +303,28 @@ def case_wireframe():
     print('wireframe:', out['wires1'].shape, 'wire pixels', changed, os.path.getsize(path), 'B')
 
 
+def case_postfx():
+    """postp/fxaa.py and postp/blooming.py on a synthetic HDR image (particles_ prefix = not a raster scene)."""
+    ti = tina.ti
+    rng = np.random.default_rng(3)
+    W, H = 72, 50
+    img = (rng.random((W, H, 3)) ** 3 * 3).astype(np.float32)
+    img[20:40, 10:30] += np.float32(2.5)  # a bright block: blooming threshold 1, strong FXAA edges
+    fld = ti.Vector.field(3, float, (W, H))
+    fld.from_numpy(img)
+    fx = tina.FXAA((W, H))
+    fx.apply(fld)
+    out = {'input': img, 'fxaa': fld.to_numpy().astype(np.float32)}
+    fld.from_numpy(img)
+    bl = tina.Blooming((W, H))
+    bl.apply(fld)
+    out['bloom'] = fld.to_numpy().astype(np.float32)
+    out['gwei'] = bl.gwei.to_numpy()[:int(bl.radius[None]) + 1].astype(np.float32)
+    path = os.path.join(HERE, 'particles_postfx.npz')
+    np.savez_compressed(path, **out)
+    print('postfx: fxaa changed', int((np.abs(out['fxaa'] - img).max(-1) > 0).sum()), 'bloom mean', float((out['bloom'] - img).mean()))
+
+
 if __name__ == '__main__':
     np.seterr(all='ignore')
     case_monkey()
@@ -314,3 +336,4 @@ if __name__ == '__main__':
     case_gbuffers()
     case_particles()
     case_wireframe()
+    case_postfx()

@@ -217,3 +217,15 @@ def test_oracle_wireframe_matches_reference_sources(tina, O):
     assert np.array_equal(depth, g['depth_after1'])
     assert np.abs(image - g['image_after1']).max() <= COLOR_TOL
     assert (g['depth_after1'] != g['depth_after0']).sum() > 500
+
+
+def test_oracle_postfx_match_reference_sources(tina, O):
+    """postp/fxaa.py, postp/blooming.py under the shim: oracle restatements identical, Gaussian weights too."""
+    g = np.load(os.path.join(GOLDEN, 'particles_postfx.npz'))
+    assert np.array_equal(O.fxaa(g['input']), g['fxaa'])
+    W, H = g['input'].shape[:2]
+    gw = tina.Blooming((W, H)).gaussian_weights()
+    # (x**2 of a runtime scalar: powf in the shim's numpy vs x*x here; Taichi's own lowering is unpinned) -> 1 ulp
+    assert np.abs(gw - g['gwei']).max() <= 2e-8
+    assert np.array_equal(O.bloom(g['input'], g['gwei']), g['bloom'])
+    assert np.abs(O.bloom(g['input'], gw) - g['bloom']).max() <= 1e-6

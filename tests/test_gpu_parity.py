@@ -683,3 +683,41 @@ def test_wireframe_raster_matches_reference_golden(tina, O):
                                   color=(0.1, 0.7, 0.3), clipping=clipping)
         assert np.array_equal(engine.depth.to_numpy(), d), clipping
         assert np.array_equal(img.to_numpy(), im), clipping
+
+
+def test_postfx_fxaa_and_blooming(tina, O):
+    """§8f row 4 (deterministic half): FXAA and Blooming kernels against the golden produced by the reference's
+    own sources, and inside Scene.render (raster.py:200-205 order: bloom -> tonemap -> fxaa) against the oracle."""
+    import os
+    import torch
+    from test_golden import GOLDEN
+    g = np.load(os.path.join(GOLDEN, 'particles_postfx.npz'))
+    W, H = g['input'].shape[:2]
+    t = torch.as_tensor(g['input']).cuda()
+    tina.FXAA((W, H)).apply(tina.Field(t))
+    assert np.array_equal(t.cpu().numpy(), g['fxaa'])
+    t = torch.as_tensor(g['input']).cuda()
+    tina.Blooming((W, H)).apply(tina.Field(t))
+    assert np.abs(t.cpu().numpy() - g['bloom']).max() <= 1e-6
+    # in a scene: strong light so that the highlights exceed the bloom threshold
+    W, H = 160, 120
+    view, proj = scenes.default_camera(W / H)
+    tri = scenes.soup(600, W, H, s=0.1, seed=3)
+    imgs = {}
+    for fx in (False, True):
+        scene = tina.Scene((W, H), blooming=True, fxaa=fx)
+        mesh = tina.SimpleMesh()
+        mesh.set_face_verts(tri)
+        scene.add_object(mesh, tina.Classic())
+        scene.lighting.add_light(dir=[0, 0, 1], color=[6, 5, 4])
+        scene.engine.set_camera(view, proj)
+        scene.render()
+        torch.cuda.synchronize()
+        imgs[fx] = scene.img.to_numpy()
+    ref = O.render_scene([(tri, None, None, tina.Classic())], W, H, view, proj, scene.lighting, _flags(O), do_tonemap=False)
+    assert ref['image'].max() > 1.5
+    img = O.tonemap(O.bloom(ref['image'], scene.blooming.gaussian_weights()))
+    assert np.abs(imgs[False] - img).max() <= COLOR_TOL
+    # FXAA branches on thresholds, so it is checked on identical input: the oracle filter applied to this
+    # pipeline's own pre-FXAA frame must reproduce the fxaa=True frame bit for bit
+    assert np.array_equal(imgs[True], O.fxaa(imgs[False]))
