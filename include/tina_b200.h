@@ -196,7 +196,13 @@ int tina_raster_buffers(TinaRaster *r, const float **verts, const float **norms,
  * 10 = programmatic dependent launch of k_raster_faces / k_render_color on/off,
  * 11 = indexed (per-unique-vertex) path for MeshGrid / MeshModel sources on/off,
  * 12 = adaptive tile path: after 8 consecutive render_occup/render_color pairs that queued no large
- *      face the tile-path kernel is not launched and the setup kernel walks large faces itself */
+ *      face the tile-path kernel is not launched and the setup kernel walks large faces itself,
+ * 13 = fast shading (default 1): render_color keeps the barycentric weights in the reference's exact
+ *      arithmetic but evaluates interpolation, normalisation, the view ray, lighting and the tone curve
+ *      with FMA contraction and SFU rcp/rsqrt (colour within 1e-4 of the reference, ids/depth unaffected).
+ *      Applies to constant-brdf and Lambert+Phong (constant shineness <= 64) materials; Cook-Torrance and
+ *      interpreted programs always shade exactly;
+ *      0 = every shading op in the reference's order with IEEE division/sqrt */
 int tina_raster_set_tuning(TinaRaster *r, int which, int value);
 /* counters of the last render_occup (synchronises): faces culled, clipped, per-thread,
  * per-warp, queued for the tile path, tile-list entries */

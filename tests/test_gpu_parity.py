@@ -395,13 +395,53 @@ def test_specialised_shading_equals_interpreter(tina, O):
             scene.add_object(mesh, mat)
             scene.engine.set_camera(view, proj)
             scene.lighting.add_light(pos=[0.5, 0.5, 2.0], color=[0.3, 0.6, 0.9])
-            scene.triangle_raster.set_tuning(generic_vm=generic)
+            scene.triangle_raster.set_tuning(generic_vm=generic, fast_shading=0)
             scene.render()
             torch.cuda.synchronize()
             imgs.append(scene.img.to_numpy())
         assert np.array_equal(imgs[0], imgs[1])
         ref = O.render_scene([(tri, nrm, None, mat)], W, H, view, proj, scene.lighting, _flags(O, smoothing=True), do_tonemap=False)
         assert np.abs(imgs[0] - ref['image']).max() <= COLOR_TOL
+        # default (fast) shading: same pixels, colour inside the tolerance
+        scene.triangle_raster.set_tuning(generic_vm=0, fast_shading=1)
+        scene.render()
+        torch.cuda.synchronize()
+        assert np.abs(scene.img.to_numpy() - ref['image']).max() <= COLOR_TOL
+
+
+def test_fast_shading_stays_within_colour_tolerance(tina, O):
+    """render_color's default arithmetic (FMA + SFU rcp/rsqrt downstream of the exact barycentric weights) against
+    its exact arm and against the oracle, on the C2-style grid (Classic) and a sliver-rich soup (Diffuse, flat)."""
+    import torch
+    W, H = 640, 360
+    view, proj = scenes.default_camera(W / H)
+    worst = 0.0
+    for kind in ('grid', 'soup'):
+        imgs = {}
+        for fast in (0, 1):
+            if kind == 'grid':
+                scene = tina.Scene((W, H), smoothing=True)
+                mesh = tina.MeshGrid(96)
+                mesh.pos.from_numpy(scenes.wave_grid_pos(96))
+                scene.add_object(mesh, tina.Classic())
+            else:
+                scene = tina.Scene((W, H))
+                mesh = tina.SimpleMesh()
+                mesh.set_face_verts(scenes.soup(5000, W, H, s=0.02, seed=11))
+                scene.add_object(mesh, tina.Diffuse())
+            scene.engine.set_camera(view, proj)
+            scene.triangle_raster.set_tuning(fast_shading=fast)
+            scene.render()
+            torch.cuda.synchronize()
+            imgs[fast] = scene.img.to_numpy()
+            keys = scene.engine.keys.clone()
+            if fast == 0:
+                keys0 = keys
+        assert torch.equal(keys, keys0)
+        d = float(np.abs(imgs[0] - imgs[1]).max())
+        worst = max(worst, d)
+        assert d <= 2e-5, (kind, d)
+    print('fast-vs-exact shading max abs colour difference', worst)
 
 
 def _golden_cases():

@@ -29,4 +29,7 @@ for rep in range(2):
             ts.append((a, b))
         torch.cuda.synchronize()
         t = np.array([a.elapsed_time(b) for a, b in ts]) * 1e3
-        print(f'{knob}={v}: median {np.median(t):.1f} us  min {t.min():.1f} us')
+        raster.set_tuning(profile=1); step(); torch.cuda.synchronize()
+        kt = {k: round(x * 1e3, 1) for k, x in raster.kernel_times().items() if x > 0}
+        raster.set_tuning(profile=0)
+        print(f'{knob}={v}: median {np.median(t):.1f} us  min {t.min():.1f} us  kernels(us) {kt}', flush=True)
