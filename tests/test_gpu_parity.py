@@ -761,3 +761,54 @@ def test_postfx_fxaa_and_blooming(tina, O):
     # FXAA branches on thresholds, so it is checked on identical input: the oracle filter applied to this
     # pipeline's own pre-FXAA frame must reproduce the fxaa=True frame bit for bit
     assert np.array_equal(imgs[True], O.fxaa(imgs[False]))
+
+
+@pytest.mark.parametrize('seed', range(8))
+def test_fuzz_random_scenes_ids_depth_bit_exact(tina, O, seed):
+    """Random resolutions (1x1 ... odd, not multiples of the 16-px tiles or 256-px chunks), random cameras (also
+    inside the geometry, so w <= 0 and huge projected faces occur), face sizes over six decades, duplicated /
+    shared-vertex faces, random flags and sample bias -- expanded (SimpleMesh) and indexed (MeshModel) sources
+    against the oracle: ids and depth bit for bit, colour inside the tolerance wherever the oracle is finite."""
+    import torch
+    rng = np.random.default_rng(1000 + seed)
+    W, H = [(1, 1), (37, 53), (257, 3), (16, 16), (300, 17), (129, 255), (64, 500), (511, 97)][seed]
+    nv = int(rng.integers(20, 400))
+    scale = 10.0 ** rng.uniform(-3, 1, (nv, 1))
+    v = (rng.normal(0, 1, (nv, 3)) * scale).astype(np.float32)
+    v[rng.integers(0, nv, 5)] = v[rng.integers(0, nv, 5)]          # coincident vertices
+    nf = int(rng.integers(50, 3000))
+    f = rng.integers(0, nv, (nf, 3))
+    f[rng.integers(0, nf, 10)] = f[rng.integers(0, nf, 10)]        # duplicated faces (exact depth ties)
+    f[rng.integers(0, nf, 5), 1] = f[rng.integers(0, nf, 5), 0]    # degenerate (repeated index)
+    eye = rng.normal(0, 1.5, 3)
+    view = tina.lookat(pos=eye.tolist(), back=rng.normal(0, 1, 3).tolist(), up=[0, 1, 0.1])
+    proj = tina.perspective(fov=float(rng.uniform(20, 120)), aspect=W / H, near=float(10.0 ** rng.uniform(-3, -0.5)), far=500.0)
+    view, proj = np.asarray(view, np.float32), np.asarray(proj, np.float32)
+    bias = tuple(rng.uniform(0, 1, 2).astype(np.float32).tolist()) if seed % 2 else (0.5, 0.5)
+    culling, clipping = bool(rng.integers(0, 2)), bool(rng.integers(0, 2))
+    tri = np.ascontiguousarray(v[f])
+    ref = None
+    for source in ('expanded', 'indexed'):
+        scene = tina.Scene((W, H), culling=culling, clipping=clipping, maxfaces=nf)
+        if source == 'expanded':
+            mesh = tina.SimpleMesh(maxfaces=nf)
+            mesh.set_face_verts(tri)
+        else:
+            mesh = tina.MeshModel(dict(v=v, f=np.stack([f, np.zeros_like(f), np.zeros_like(f)], axis=2),
+                                       vn=np.float32([[0, 0, 1]]), vt=np.float32([[0, 0]])))
+        scene.add_object(mesh)
+        scene.engine.set_camera(view, proj)
+        scene.engine.bias[None] = bias
+        scene.render()
+        torch.cuda.synchronize()
+        if ref is None:
+            with np.errstate(all='ignore'):
+                ref = O.render_scene([(tri, None, None, tina.Diffuse())], W, H, view, proj, scene.lighting,
+                                     _flags(O, culling=culling, clipping=clipping), bias=bias)
+        assert np.array_equal(scene.engine.depth.to_numpy(), ref['depth']), (source, W, H)
+        assert np.array_equal(scene.triangle_raster.occup.to_numpy(), ref['occups'][-1]), (source, W, H)
+        img, rimg = scene.img.to_numpy(), ref['image']
+        ok = np.isfinite(rimg)
+        assert np.array_equal(np.isfinite(img), ok)
+        if ok.any():
+            assert np.abs(img[ok] - rimg[ok]).max() <= COLOR_TOL
