@@ -23,4 +23,5 @@ from .postp import FXAA, Blooming
 from .scene import Scene
 from .control import Control, RotationStep
 from .field import Field
+from .graph import FrameGraph
 from . import multigpu

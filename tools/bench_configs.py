@@ -49,6 +49,7 @@ def main():
     ap.add_argument('--tiny-max', type=int, nargs='*', default=[None])
     ap.add_argument('--faces', type=int, default=None)
     ap.add_argument('--views', type=int, default=64)
+    ap.add_argument('--graph', action='store_true', help='c1/c4: record the step into a CUDA graph and time replays')
     ap.add_argument('--partitioned', action='store_true', help='c5: partitioned attributes + all-reduce composite')
     args = ap.parse_args()
     import __graft_entry__ as g
@@ -84,8 +85,9 @@ def main():
             if tm is not None:
                 raster.set_tuning(tiny_max=tm)
             step()
-            med, mn = timed(step, args.iters, flush, world)
-            say(config='c1', faces=968, res=[W, H], tiny_max=tm, ms=med, ms_min=mn, frames_per_s=1e3 / med, mtris_per_s=968 / med / 1e3)
+            run = tina.FrameGraph(step).replay if args.graph else step
+            med, mn = timed(run, args.iters, flush, world)
+            say(config='c1', graph=bool(args.graph), faces=968, res=[W, H], tiny_max=tm, ms=med, ms_min=mn, frames_per_s=1e3 / med, mtris_per_s=968 / med / 1e3)
 
     elif args.config == 'c3':
         W, H = 3840, 2160
@@ -147,8 +149,9 @@ def main():
                 scene.engine.set_camera(*cams[k])
                 scene.render()
         step()
-        med, mn = timed(step, args.iters, flush, world)
-        say(config='c4', views=len(cams), gpus=world, res=[W, H], ms=med, ms_min=mn, views_per_s=len(cams) / med * 1e3,
+        run = tina.FrameGraph(step).replay if args.graph else step
+        med, mn = timed(run, args.iters, flush, world)
+        say(config='c4', graph=bool(args.graph), views=len(cams), gpus=world, res=[W, H], ms=med, ms_min=mn, views_per_s=len(cams) / med * 1e3,
             ms_per_view_per_gpu=med / max(1, len(mine)))
 
     elif args.config == 'c5':
