@@ -35,7 +35,7 @@ sys.path.insert(0, os.path.join(ROOT, 'tests'))
 import numpy as np  # noqa: E402
 
 
-def ncu_traffic(kernel_file='r1_v6_k_raster_faces_indexed_ncu.txt'):
+def ncu_traffic(kernel_file='r1_v9_k_raster_faces_ncu.txt'):
     """DRAM bytes (read + write) per launch of the dominant kernel from the committed `ncu --set full` summary
     under profiles/ (tools/ncu_summary.py output).  None if the file is missing."""
     p = os.path.join(ROOT, 'profiles', kernel_file)
@@ -267,12 +267,15 @@ def run_ours(args):
     K = args.steps
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     barrier()
+    from taichi_three_b200 import _lib as _tl
+    launches0 = int(_tl.lib().tina_launch_count())
     wall0 = time.perf_counter()
     for a, b in evs:
         flush_l2()
         a.record()
         step()
         b.record()
+    my_launches = int(_tl.lib().tina_launch_count()) - launches0  # this library's kernels inside the timed steps
     barrier()
     wall = time.perf_counter() - wall0
     step_ms = np.array([a.elapsed_time(b) for a, b in evs])
@@ -409,14 +412,17 @@ def run_ours(args):
             'kernel_ms': kmean,
             'roofline': {'bound': 'hbm', 'kernel': 'k_raster_faces', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                          'frac': achieved / peak, 'traffic': ncu_traffic() if wl == 'c2' else None,
-                         'traffic_source': 'profiles/r1_v6_k_raster_faces_indexed_ncu.txt (ncu --set full, dram read+write per launch)',
+                         'traffic_source': 'profiles/r1_v9_k_raster_faces_ncu.txt (ncu --set full, dram read+write per launch)',
+                         'note': 'issue-bound kernel: ncu smsp__issue_active 80 %, DRAM 6 % of peak (same file)',
                          'alg_bytes': k1_bytes, 'peak_source': peak_src},
             'cpu_baseline': cpu,
             'e2e': {'value': e2e_value, 'unit': 'Mtris/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'ms_per_step': e2e_s * 1e3, 'steps': Ke, 'image_checksum': checksum,
                     'frames_in_flight': 2 if e2e_pipe_s <= e2e_serial_s else 1,
                     'ms_per_step_serial': e2e_serial_s * 1e3, 'ms_per_step_2_in_flight': e2e_pipe_s * 1e3},
-            'gpu_launches': (5 if w['kind'] != 'soup' else 4) * K,  # k_clear_keys, [k_vtx_clip], k_raster_faces, k_large_path, k_render_color
+            # counted by the library (tina_launch_count) on rank 0, x ranks: k_clear_keys, [k_vtx_clip], k_raster_faces,
+            # [k_large_path unless the adaptive tile path is skipping it], k_render_color per step
+            'gpu_launches': my_launches * world,
             'clocks': clocks,
         }
         print(json.dumps(line), flush=True)

@@ -55,6 +55,8 @@ typedef struct TinaRaster TinaRaster;
 #define TINA_MAX_LIGHTS 16 /* lighting.py:26 */
 #define TINA_MAX_INSTR 96
 #define TINA_MAX_TEX 4
+#define TINA_MAX_PEERS 16        /* ranks of one node whose key buffers can be composited over peer memory */
+#define TINA_IPC_HANDLE_BYTES 64 /* sizeof(cudaIpcMemHandle_t) */
 
 /* Lighting (lighting.py:25-98).  dirs[i] = (x,y,z,w): w=0 directional (already
  * normalised by the host, lighting.py:60-62), w=1 point light. */
@@ -106,6 +108,8 @@ typedef struct {
 
 const char *tina_last_error(void);
 int tina_version(void);
+/* number of kernels this library has launched in this process (all engines, all streams); for benchmarks */
+uint64_t tina_launch_count(void);
 
 /* ---- Engine (core/engine.py) ------------------------------------------------ */
 /* engine.py:6-28: owns the per-pixel key buffer (depth + winner), W2V/V2W (init
@@ -161,6 +165,29 @@ int tina_raster_render_color(TinaRaster *r, const TinaMaterial *mat_host, const 
 int tina_raster_render_color_range(TinaRaster *r, const TinaMaterial *mat_host, const TinaLighting *light_host,
                                    float *image, uint32_t flags, const float *bg_host, int64_t first_pixel, int64_t npixels,
                                    uint32_t face_base, void *stream);
+/* Sort-last over peer memory (no counterpart in the reference): every rank of one node rasterises its
+ * face range into its own engine; tina_engine_ipc_export gives a CUDA IPC handle of the engine's key buffer,
+ * tina_engine_ipc_open_peers maps the buffers of all `world` ranks (handles_host = world x 64 bytes in rank order;
+ * entry `rank` is ignored).  tina_raster_render_color_composite then shades pixels [first_pixel, first_pixel +
+ * npixels) like render_color_range, but takes each pixel's key as the MIN over all ranks' buffers, read over
+ * NVLink inside the shading kernel, and stores the composited key in the local buffer.  The caller orders it
+ * after every rank's render_occup (any collective on the same stream, e.g. a barrier) and keeps the next
+ * clear_depth behind every rank's composite (the all-gather of the image strips does that). */
+int tina_engine_ipc_export(TinaEngine *e, uint8_t *handle64_host);
+int tina_engine_ipc_open_peers(TinaEngine *e, const uint8_t *handles_host, int world, int rank);
+int tina_engine_ipc_close_peers(TinaEngine *e);
+/* the same table from plain device pointers (engines of one process: several engines on one GPU, or several GPUs
+ * with peer access enabled); keys_host[rank] is ignored, the pointers stay owned by the caller */
+int tina_engine_set_peer_keys(TinaEngine *e, int64_t *const *keys_host, int world, int rank);
+int tina_raster_render_color_composite(TinaRaster *r, const TinaMaterial *mat_host, const TinaLighting *light_host,
+                                       float *image, uint32_t flags, const float *bg_host, int64_t first_pixel,
+                                       int64_t npixels, uint32_t face_base, void *stream);
+/* A device buffer one rank allocates and the other ranks of the node map (CUDA IPC): the frame image the ranks'
+ * shading kernels store their strips into directly (sort-last with the image assembled on one rank, no gather). */
+int tina_shared_alloc(int device, int64_t bytes, void **ptr, uint8_t *handle64_host);
+int tina_shared_free(int device, void *ptr);
+int tina_shared_open(int device, const uint8_t *handle64_host, void **ptr);
+int tina_shared_close(int device, void *ptr);
 /* G-buffer sinks of core/shader.py:21-109 for the current object (ShaderGroup fan-out, shader.py:138-148):
  * writes `ncomp` (1..3) float32 (or int32 if out_is_int) values per pixel where the object is visible,
  * out[(x*H + y)*ncomp + k].  param_host: ConstShader value (3 floats) / ChessboardShader size (1 float). */

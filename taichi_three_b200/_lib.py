@@ -46,6 +46,7 @@ _fp = C.POINTER(C.c_float)
 SIGNATURES = {
     'tina_last_error': (C.c_char_p, []),
     'tina_version': (_i, []),
+    'tina_launch_count': (C.c_uint64, []),
     'tina_engine_create': (_i, [C.POINTER(_vp), _i, _i, _i]),
     'tina_engine_destroy': (_i, [_vp]),
     'tina_engine_set_camera': (_i, [_vp, _fp, _fp]),
@@ -55,6 +56,10 @@ SIGNATURES = {
     'tina_engine_depth': (_i, [_vp, _vp, _vp]),
     'tina_engine_set_face_base': (_i, [_vp, _u32]),
     'tina_engine_get_face_base': (_i, [_vp, C.POINTER(_u32)]),
+    'tina_engine_ipc_export': (_i, [_vp, _vp]),
+    'tina_engine_ipc_open_peers': (_i, [_vp, _vp, _i, _i]),
+    'tina_engine_ipc_close_peers': (_i, [_vp]),
+    'tina_engine_set_peer_keys': (_i, [_vp, C.POINTER(_vp), _i, _i]),
     'tina_raster_create': (_i, [C.POINTER(_vp), _vp, _i64, _u32]),
     'tina_raster_destroy': (_i, [_vp]),
     'tina_raster_set_faces': (_i, [_vp, _vp, _vp, _vp, _i64, _i, _vp]),
@@ -65,6 +70,12 @@ SIGNATURES = {
     'tina_raster_render_color': (_i, [_vp, C.POINTER(TinaMaterial), C.POINTER(TinaLighting), _vp, _u32, _fp, _vp]),
     'tina_raster_render_color_range': (_i, [_vp, C.POINTER(TinaMaterial), C.POINTER(TinaLighting), _vp, _u32, _fp, _i64, _i64,
                                              _u32, _vp]),
+    'tina_raster_render_color_composite': (_i, [_vp, C.POINTER(TinaMaterial), C.POINTER(TinaLighting), _vp, _u32, _fp, _i64,
+                                                 _i64, _u32, _vp]),
+    'tina_shared_alloc': (_i, [_i, _i64, C.POINTER(_vp), _vp]),
+    'tina_shared_free': (_i, [_i, _vp]),
+    'tina_shared_open': (_i, [_i, _vp, C.POINTER(_vp)]),
+    'tina_shared_close': (_i, [_i, _vp]),
     'tina_raster_render_gbuffer': (_i, [_vp, _i, _vp, _i, _i, _fp, _vp]),
     'tina_raster_occup': (_i, [_vp, _vp, _vp]),
     'tina_raster_buffers': (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i64)]),

@@ -87,6 +87,31 @@ class Engine:
         """Offset of the next render_occup's face ids (sort-last multi-GPU: global ids)."""
         _lib.check(_lib.lib().tina_engine_set_face_base(self._h, int(base)))
 
+    def open_peer_keys(self, group=None):
+        """Map the key buffers of every rank of `group` (one node) into this engine through CUDA IPC, for
+        TriangleRaster.render_color_composite (sort-last composite over NVLink peer memory).  Collective."""
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        mine = (C.c_uint8 * 64)()
+        _lib.check(_lib.lib().tina_engine_ipc_export(self._h, mine))
+        t = torch.tensor(list(mine), dtype=torch.uint8, device=self.keys.device)
+        allh = torch.empty(world * 64, dtype=torch.uint8, device=t.device)
+        dist.all_gather_into_tensor(allh, t, group=group)
+        buf = (C.c_uint8 * (world * 64))(*allh.cpu().tolist())
+        _lib.check(_lib.lib().tina_engine_ipc_open_peers(self._h, buf, world, rank))
+        self._peers = world
+
+    def set_peer_keys(self, engines, rank):
+        """Same table from engines of this process (e.g. several engines on one GPU): engines[rank] is self."""
+        ptrs = (C.c_void_p * len(engines))(*[e.keys.data_ptr() for e in engines])
+        _lib.check(_lib.lib().tina_engine_set_peer_keys(self._h, ptrs, len(engines), int(rank)))
+        self._peers = len(engines)
+        self._peer_refs = list(engines)
+
+    def close_peer_keys(self):
+        _lib.check(_lib.lib().tina_engine_ipc_close_peers(self._h))
+        self._peers = 0
+
     @property
     def face_base(self):
         v = C.c_uint32()

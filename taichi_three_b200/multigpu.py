@@ -60,12 +60,54 @@ def strip_range(npix, rank, world):
     return min(rank * per * 256, npix), min((rank + 1) * per * 256, npix)
 
 
-def render_sort_last_replicated(engine, raster, verts, norms, coors, shader, bgcolor=0.0, group=None):
+class SharedImage:
+    """A float32 [W, H, 3] frame image that lives on rank `root` and is mapped into every rank of the node
+    (CUDA IPC): the ranks' shading kernels store their screen strips straight into it over NVLink, so a sort-last
+    frame needs no gather.  `.tensor` is the image (the root's memory on every rank).  Collective constructor."""
+
+    def __init__(self, res, group=None, root=0):
+        import ctypes as C
+        from . import _lib
+        from .field import wrap_device
+        self.group, self.root = group, root
+        self.rank = dist.get_rank(group)
+        self.device = torch.device('cuda', torch.cuda.current_device())
+        self._ptr = C.c_void_p()
+        nbytes = int(res[0]) * int(res[1]) * 3 * 4
+        handle = (C.c_uint8 * 64)()
+        if self.rank == root:
+            _lib.check(_lib.lib().tina_shared_alloc(self.device.index, nbytes, C.byref(self._ptr), handle))
+        t = torch.tensor(list(handle), dtype=torch.uint8, device=self.device)
+        dist.broadcast(t, src=dist.get_global_rank(group, root) if group is not None else root, group=group)
+        if self.rank != root:
+            buf = (C.c_uint8 * 64)(*t.cpu().tolist())
+            _lib.check(_lib.lib().tina_shared_open(self.device.index, buf, C.byref(self._ptr)))
+        self.tensor = wrap_device(self._ptr.value, (int(res[0]), int(res[1]), 3), torch.float32, self.device, owner=self)
+
+    def close(self):
+        from . import _lib
+        if getattr(self, '_ptr', None) and self._ptr.value:
+            dist.barrier(group=self.group)  # nobody is still writing into the root's buffer
+            if self.rank == self.root:
+                _lib.lib().tina_shared_free(self.device.index, self._ptr)
+            else:
+                _lib.lib().tina_shared_close(self.device.index, self._ptr)
+            self._ptr = None
+
+
+def render_sort_last_replicated(engine, raster, verts, norms, coors, shader, bgcolor=0.0, group=None, composite='nccl', gather='all'):
     """Sort-last frame with REPLICATED face attributes (every rank holds all N faces, C5: 4.8 GB):
     rank r rasterises faces face_range(N, r, G) with global ids, the keys are MIN-reduce-scattered so
     rank r ends up with the final keys of screen strip r (1/G of the all-reduce traffic), shades that
     strip from the full attribute arrays, and the image strips are all-gathered.  Bit-identical to one
-    GPU.  Needs W*H divisible by 256*G (else falls back to the all-reduce composite)."""
+    GPU.  Needs W*H divisible by 256*G (else falls back to the all-reduce composite).
+
+    composite='p2p' (after engine.open_peer_keys(group), ranks of one node): no reduce-scatter at all -- after a
+    barrier the strip's shading kernel takes each pixel's key as the MIN over all ranks' key buffers, read over NVLink
+    peer memory inside the kernel (TriangleRaster.render_color_composite).  Same bits.
+
+    gather='root' (shader.img wraps a SharedImage tensor): the image is assembled on the root rank only, by the
+    shading kernels' own stores over NVLink; no all-gather."""
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     N = verts.shape[0]
@@ -89,12 +131,26 @@ def render_sort_last_replicated(engine, raster, verts, norms, coors, shader, bgc
         raster.set_face_coors(coors)
     if world > 1 and npix % (256 * world) == 0:
         p_lo, p_hi = strip_range(npix, rank, world)
-        strip = torch.empty(p_hi - p_lo, dtype=torch.int64, device=keys.device)
-        dist.reduce_scatter_tensor(strip, keys, op=dist.ReduceOp.MIN, group=group)
-        keys[p_lo:p_hi] = strip
-        raster.render_color_range(shader, p_lo, p_hi - p_lo, face_base=0, fill_bg=bgcolor)
-        flat = img.view(-1)
-        dist.all_gather_into_tensor(flat, flat[p_lo * 3:p_hi * 3].clone(), group=group)
+        if composite == 'p2p':
+            # a one-word all-reduce on the same stream: it completes on this rank only after every rank has
+            # enqueued it behind its own render_occup (dist.barrier() would also block the host)
+            tok = torch.zeros(1, dtype=torch.int32, device=keys.device)
+            dist.all_reduce(tok, group=group)
+            raster.render_color_composite(shader, p_lo, p_hi - p_lo, face_base=0, fill_bg=bgcolor)
+        else:
+            strip = torch.empty(p_hi - p_lo, dtype=torch.int64, device=keys.device)
+            dist.reduce_scatter_tensor(strip, keys, op=dist.ReduceOp.MIN, group=group)
+            keys[p_lo:p_hi] = strip
+            raster.render_color_range(shader, p_lo, p_hi - p_lo, face_base=0, fill_bg=bgcolor)
+        if gather == 'root':
+            # shader.img is a SharedImage: the strip has been stored into the root's memory by the shading kernel.
+            # One-word all-reduce = end-of-frame fence: the root's image is complete, and no rank clears its keys
+            # while a peer still reads them.
+            tok = torch.zeros(1, dtype=torch.int32, device=keys.device)
+            dist.all_reduce(tok, group=group)
+        else:
+            flat = img.view(-1)
+            dist.all_gather_into_tensor(flat, flat[p_lo * 3:p_hi * 3].clone(), group=group)
     else:
         composite_min(keys, group)
         raster.render_color_range(shader, 0, npix, face_base=0, fill_bg=bgcolor)

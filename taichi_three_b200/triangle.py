@@ -180,6 +180,21 @@ class TriangleRaster:
                                                              _stream(self._dev_index)))
         self._mat_keep = keep
 
+    def render_color_composite(self, shader, first_pixel, npixels, face_base=0, fill_bg=None):
+        """render_color_range whose keys are the MIN over the key buffers of all ranks mapped by
+        Engine.open_peer_keys(), read over NVLink inside the shading kernel (sort-last composite fused with shading).
+        The caller orders it after every rank's render_occup (e.g. dist.barrier() on the same stream)."""
+        if not isinstance(shader, Shader):
+            raise NotImplementedError('render_color_composite takes a single Shader')
+        t = shader.img.to_torch() if hasattr(shader.img, 'to_torch') else shader.img
+        mat, keep = self._material_struct(shader.material)
+        flags = _lib.TINA_COLOR_FILL_BG if fill_bg is not None else 0
+        bg = _fp(np.broadcast_to(np.asarray(fill_bg if fill_bg is not None else 0, dtype=np.float32), (3,)))
+        _lib.check(_lib.lib().tina_raster_render_color_composite(self._h, mat, shader.lighting.struct_ref(), C.c_void_p(t.data_ptr()),
+                                                                 flags, bg, int(first_pixel), int(npixels), int(face_base),
+                                                                 _stream(self._dev_index)))
+        self._mat_keep = keep
+
     def _render_sink(self, s, st):
         """G-buffer shaders (shader.py:21-109) for the current object."""
         t = s.img.to_torch() if hasattr(s.img, 'to_torch') else s.img

@@ -846,3 +846,54 @@ def test_frame_graph_replay_equals_eager(tina, O):
     d, o = tina.multigpu.unpack_keys(keys_g.cpu().view(W, H))
     first = (o.numpy() >= 0) & (o.numpy() < fv.shape[0])
     assert np.array_equal(d.numpy()[first], ref[1][first]) and np.array_equal(o.numpy()[first], ref[0][first])
+
+
+def test_peer_memory_composite_equals_single_engine(tina, O):
+    """Sort-last composite fused into the shading kernel (render_color_composite): two engines rasterise disjoint
+    face ranges with global ids; each shades one screen strip taking every key as the MIN over both key buffers.
+    Keys and image must equal one engine rendering all faces.  (Across processes / GPUs the same table is filled
+    through CUDA IPC, tools/bench_configs.py c5 --p2p.)"""
+    import torch
+    W, H, n = 512, 256, 20000
+    view, proj = scenes.default_camera(W / H)
+    tri = torch.as_tensor(scenes.soup(n, W, H, s=0.02, seed=21)).cuda()
+    lighting = tina.Lighting()
+    lighting.add_light(dir=[1, 2, 3], color=[0.9, 0.9, 0.9])
+    lighting.set_ambient_light([0.1, 0.1, 0.1])
+
+    def setup():
+        e = tina.Engine((W, H))
+        e.set_camera(view, proj)
+        r = tina.TriangleRaster(e, maxfaces=n)
+        img = tina.Field(torch.zeros((W, H, 3), device='cuda'))
+        return e, r, tina.Shader(img, lighting, tina.Diffuse())
+
+    e0, r0, s0 = setup()
+    e0.clear_depth()
+    r0.set_face_verts(tri)
+    r0.render_occup()
+    r0.render_color(s0, fill_bg=np.float32([0.1, 0.2, 0.3]))
+    parts = [setup() for _ in range(2)]
+    engines = [p[0] for p in parts]
+    cut = 7777
+    for k, (e, r, s) in enumerate(parts):
+        lo, hi = (0, cut) if k == 0 else (cut, n)
+        e.clear_depth()
+        e.set_face_base(lo)
+        r.set_face_verts(tri[lo:hi])
+        r.render_occup()
+        e.set_peer_keys(engines, k)
+    npix = W * H
+    half = (npix // 2) // 256 * 256
+    out = torch.zeros((W, H, 3), device='cuda')
+    for k, (e, r, s) in enumerate(parts):
+        r.set_face_verts(tri)  # the full arrays for shading (ids in the keys are global)
+        p_lo, p_hi = (0, half) if k == 0 else (half, npix)
+        r.render_color_composite(s, p_lo, p_hi - p_lo, face_base=0, fill_bg=np.float32([0.1, 0.2, 0.3]))
+        out.view(-1)[p_lo * 3:p_hi * 3] = s.img.to_torch().view(-1)[p_lo * 3:p_hi * 3]
+    torch.cuda.synchronize()
+    assert torch.equal(out, s0.img.to_torch())
+    comp = torch.cat([engines[0].keys.view(-1)[:half], engines[1].keys.view(-1)[half:]])
+    assert torch.equal(comp, e0.keys.view(-1))
+    for e in engines:
+        e.close_peer_keys()

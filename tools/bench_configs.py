@@ -50,6 +50,8 @@ def main():
     ap.add_argument('--faces', type=int, default=None)
     ap.add_argument('--views', type=int, default=64)
     ap.add_argument('--graph', action='store_true', help='c1/c4: record the step into a CUDA graph and time replays')
+    ap.add_argument('--p2p', action='store_true', help='c5: composite over NVLink peer memory inside the shading kernel')
+    ap.add_argument('--root', action='store_true', help='c5: assemble the image on rank 0 only (strips stored over NVLink by the shading kernels)')
     ap.add_argument('--partitioned', action='store_true', help='c5: partitioned attributes + all-reduce composite')
     args = ap.parse_args()
     import __graft_entry__ as g
@@ -168,23 +170,30 @@ def main():
         lighting = tina.Lighting()
         lighting.add_light(dir=[1, 2, 3], color=[0.9, 0.9, 0.9])
         lighting.set_ambient_light([0.1, 0.1, 0.1])
-        img = tina.Field(torch.zeros((W, H, 3), device=dev))
+        shared = M.SharedImage((W, H)) if (args.root and world > 1) else None
+        img = tina.Field(shared.tensor if shared is not None else torch.zeros((W, H, 3), device=dev))
         shader = tina.Shader(img, lighting, tina.Diffuse())
+
+        if args.p2p and world > 1:
+            engine.open_peer_keys()
 
         def step():
             if args.partitioned:
                 M.render_sort_last(engine, raster, tri[lo:hi], None, None, shader)
             else:
-                M.render_sort_last_replicated(engine, raster, tri, None, None, shader)
+                M.render_sort_last_replicated(engine, raster, tri, None, None, shader, composite='p2p' if args.p2p else 'nccl',
+                                              gather='root' if shared is not None else 'all')
         step()
         med, mn = timed(step, args.iters, flush, world)
-        out = dict(config='c5', faces=N, gpus=world, res=[W, H], ms=med, ms_min=mn, mtris_per_s=N / med / 1e3, frames_per_s=1e3 / med)
+        out = dict(config='c5', gather='root' if shared is not None else 'all', composite='p2p' if args.p2p else ('allreduce' if args.partitioned else 'reduce_scatter'), faces=N, gpus=world, res=[W, H], ms=med, ms_min=mn, mtris_per_s=N / med / 1e3, frames_per_s=1e3 / med)
         if args.check:
             # checksum of the composited keys and image: identical for every G
             k = engine.keys
             out['keys_checksum'] = int((k ^ (k >> 29)).sum().item())
             out['covered'] = int(((k & 0xffffffff) != 0).sum().item())
-            out['image_sum'] = float(img.to_torch().double().sum().item())
+            if world > 1:
+                dist.barrier()
+            out['image_sum'] = float(img.to_torch().double().sum().item())  # (root gather: every rank reads the root's memory)
         say(**out)
     if world > 1:
         dist.destroy_process_group()
