@@ -110,6 +110,9 @@ const char *tina_last_error(void);
 int tina_version(void);
 /* number of kernels this library has launched in this process (all engines, all streams); for benchmarks */
 uint64_t tina_launch_count(void);
+/* self-test of the shared-divisor IEEE division used by the setup code: computes `nquotients` quotients on random
+ * and structured operands both ways and returns the number that differ from __fdiv_rn (must be 0) */
+int tina_selftest_division(int device, uint64_t nquotients, uint64_t seed, uint64_t *mismatch_host);
 
 /* ---- Engine (core/engine.py) ------------------------------------------------ */
 /* engine.py:6-28: owns the per-pixel key buffer (depth + winner), W2V/V2W (init

@@ -47,6 +47,7 @@ SIGNATURES = {
     'tina_last_error': (C.c_char_p, []),
     'tina_version': (_i, []),
     'tina_launch_count': (C.c_uint64, []),
+    'tina_selftest_division': (_i, [_i, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64)]),
     'tina_engine_create': (_i, [C.POINTER(_vp), _i, _i, _i]),
     'tina_engine_destroy': (_i, [_vp]),
     'tina_engine_set_camera': (_i, [_vp, _fp, _fp]),

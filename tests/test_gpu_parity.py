@@ -897,3 +897,16 @@ def test_peer_memory_composite_equals_single_engine(tina, O):
     assert torch.equal(comp, e0.keys.view(-1))
     for e in engines:
         e.close_peer_keys()
+
+
+def test_shared_divisor_division_is_ieee(tina):
+    """The setup code divides several numbers by one divisor with the reciprocal refinement shared (div_many in
+    tina_b200.cu); it must return the bits of IEEE round-to-nearest division for every operand: 6e9 quotients
+    (random bit patterns incl. nan / inf / denormals, moderate exponents with random mantissas, quotients at and next to 1,
+    signed zeros, all-ones mantissas, reciprocals) against __fdiv_rn."""
+    import ctypes as C
+    from taichi_three_b200 import _lib
+    for seed in (1, 2):
+        bad = C.c_uint64(123)
+        _lib.check(_lib.lib().tina_selftest_division(0, 3 * 10**9, seed, C.byref(bad)))
+        assert bad.value == 0
