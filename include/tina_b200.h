@@ -232,7 +232,9 @@ int tina_raster_buffers(TinaRaster *r, const float **verts, const float **norms,
  *      with FMA contraction and SFU rcp/rsqrt (colour within 1e-4 of the reference, ids/depth unaffected).
  *      Applies to constant-brdf and Lambert+Phong (constant shineness <= 64) materials; Cook-Torrance and
  *      interpreted programs always shade exactly;
- *      0 = every shading op in the reference's order with IEEE division/sqrt */
+ *      0 = every shading op in the reference's order with IEEE division/sqrt,
+ * 14 = lean shading kernels (default 1): with fast shading, Diffuse / Classic materials whose parameters are all
+ *      constants on untextured rasters run kernels with compile-time raster flags and no operand tests */
 int tina_raster_set_tuning(TinaRaster *r, int which, int value);
 /* counters of the last render_occup (synchronises): faces culled, clipped, per-thread,
  * per-warp, queued for the tile path, tile-list entries */

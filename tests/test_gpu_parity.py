@@ -441,6 +441,11 @@ def test_fast_shading_stays_within_colour_tolerance(tina, O):
         d = float(np.abs(imgs[0] - imgs[1]).max())
         worst = max(worst, d)
         assert d <= 2e-5, (kind, d)
+        # the lean kernels (compile-time raster flags, constant operands) are the same arithmetic: same bits
+        scene.triangle_raster.set_tuning(fast_shading=1, lean_kernels=0)
+        scene.render()
+        torch.cuda.synchronize()
+        assert np.array_equal(scene.img.to_numpy(), imgs[1]), kind
     print('fast-vs-exact shading max abs colour difference', worst)
 
 
