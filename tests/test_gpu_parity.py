@@ -446,6 +446,7 @@ def test_fast_shading_stays_within_colour_tolerance(tina, O):
         scene.render()
         torch.cuda.synchronize()
         assert np.array_equal(scene.img.to_numpy(), imgs[1]), kind
+        assert torch.equal(scene.engine.keys, keys0), kind
     print('fast-vs-exact shading max abs colour difference', worst)
 
 
