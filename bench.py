@@ -35,7 +35,7 @@ sys.path.insert(0, os.path.join(ROOT, 'tests'))
 import numpy as np  # noqa: E402
 
 
-def ncu_traffic(kernel_file='r1_v9_k_raster_faces_ncu.txt'):
+def ncu_traffic(kernel_file='r1_v10_k_raster_faces_ncu.txt'):
     """DRAM bytes (read + write) per launch of the dominant kernel from the committed `ncu --set full` summary
     under profiles/ (tools/ncu_summary.py output).  None if the file is missing."""
     p = os.path.join(ROOT, 'profiles', kernel_file)
@@ -412,8 +412,8 @@ def run_ours(args):
             'kernel_ms': kmean,
             'roofline': {'bound': 'hbm', 'kernel': 'k_raster_faces', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                          'frac': achieved / peak, 'traffic': ncu_traffic() if wl == 'c2' else None,
-                         'traffic_source': 'profiles/r1_v9_k_raster_faces_ncu.txt (ncu --set full, dram read+write per launch)',
-                         'note': 'issue-bound kernel: ncu smsp__issue_active 80 %, DRAM 6 % of peak (same file)',
+                         'traffic_source': 'profiles/r1_v10_k_raster_faces_ncu.txt (ncu --set full, dram read+write per launch)',
+                         'note': 'issue-bound kernel: ncu smsp__issue_active 78 %, DRAM 6 % of peak (same file)',
                          'alg_bytes': k1_bytes, 'peak_source': peak_src},
             'cpu_baseline': cpu,
             'e2e': {'value': e2e_value, 'unit': 'Mtris/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
