@@ -325,8 +325,42 @@ def case_postfx():
     print('postfx: fxaa changed', int((np.abs(out['fxaa'] - img).max(-1) > 0).sum()), 'bloom mean', float((out['bloom'] - img).mean()))
 
 
+def case_micro():
+    """The C2 regime at golden size: sub-pixel faces.  (a) MeshGrid(56) wave on a 40x30 screen (~0.3 px per face,
+    smooth normals, Classic) -- most faces cover no sample, many samples lie within 1e-2 px of an edge;
+    (b) adversarial micro-triangles (vertices within 1e-3..1e-1 px of sample centres, needles, slivers, near-collinear;
+    tests/test_gpu_parity.py::_adversarial_triangles) with a jittered sample bias, culling on and off."""
+    import scenes
+    from test_gpu_parity import _adversarial_triangles
+    scene = tina.Scene((40, 30), smoothing=True, maxfaces=2 * 55 * 55)
+    mesh = tina.MeshGrid(56)
+    pos = scenes.wave_grid_pos(56, t=0.4)
+    mesh.pos.from_numpy(pos)
+    scene.add_object(mesh, tina.Classic())
+    camera(scene, 40 / 30)
+    np.save(os.path.join(HERE, 'micro_grid_pos.npy'), pos)
+    render_and_dump('micro_grid_wave_smooth_classic', scene, ['Classic()'])
+    W, H = 32, 24
+    import taichi_three_b200 as mine
+    view, proj = np.asarray(mine.lookat(back=(0, 0, 3)), np.float32), np.asarray(mine.perspective(60, W / H), np.float32)
+    tri = _adversarial_triangles(np.random.default_rng(77), 1500, W, H, view, proj)
+    for culling in (True, False):
+        scene = tina.Scene((W, H), culling=culling, maxfaces=len(tri))
+        m = tina.SimpleMesh(maxfaces=len(tri))
+        m.set_face_verts(tri)
+        scene.add_object(m)
+        camera(scene, W / H)
+        scene.engine.bias[None] = [0.37, 0.81]
+        render_and_dump(f'micro_adversarial_cull{int(culling)}', scene, ['Diffuse()'])
+
+
 if __name__ == '__main__':
     np.seterr(all='ignore')
+    if len(sys.argv) > 1:  # python make_golden.py micro ...  -> only these cases
+        for name in sys.argv[1:]:
+            globals()['case_' + name]()
+        sys.exit(0)
+    case_micro()
     case_monkey()
     case_grid()
     case_cornell()
