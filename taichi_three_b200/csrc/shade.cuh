@@ -1,0 +1,609 @@
+// shade.cuh -- part of the single translation unit tina_b200.cu (included once, in order): K4 k_render_color (+ material ops / interpreter, lean and fast arms, fused sort-last composite) and k_gbuffer.
+#pragma once
+
+// ------------------------------------------------------------------------------------
+// K4: deferred shading (render_color)
+// ------------------------------------------------------------------------------------
+struct V3 {
+    float x, y, z;
+};
+__device__ __forceinline__ V3 v3(float a, float b, float c) { return V3{a, b, c}; }
+__device__ __forceinline__ float dot3(V3 a, V3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+__device__ __forceinline__ V3 cross3(V3 a, V3 b) {
+    return v3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+__device__ __forceinline__ V3 normalized(V3 v) { // taichi: invlen = 1/sqrt(norm_sqr); invlen * v
+    float inv = 1.0f / sqrtf(dot3(v, v));
+    return v3(inv * v.x, inv * v.y, inv * v.z);
+}
+// ---- relaxed arithmetic for SHADING only (tina_raster_set_tuning(.., TINA_TUNE_FAST_SHADING, 1), the default):
+// colour is specified to 1e-4 (north_star), ids and depth to the bit, so everything that decides coverage --
+// and the barycentric weights, which are ill-conditioned on slivers -- keeps the reference's exact op order,
+// while the well-conditioned rest (interpolation, normalisation, view ray, lighting, tone curve) may contract
+// to FMA and use the SFU reciprocal / rsqrt (<= 2 ulp).  Exact shading stays available as the other template arm.
+__device__ __forceinline__ float rcp_fast(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float rsq_fast(float x) {
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float fdot3(V3 a, V3 b) { return fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)); }
+template <bool FAST>
+__device__ __forceinline__ V3 normalized_t(V3 v) {
+    if (!FAST) return normalized(v);
+    const float inv = rsq_fast(fdot3(v, v));
+    return v3(inv * v.x, inv * v.y, inv * v.z);
+}
+__device__ __forceinline__ V3 mapply_pos3(const float *M, float p0, float p1, float p2) {
+    float r0, r1, r2, rw;
+    mapply(M, p0, p1, p2, 1.0f, r0, r1, r2, rw);
+    return v3(fd(r0, rw), fd(r1, rw), fd(r2, rw));
+}
+
+struct ShadeIn {
+    V3 pos, color, normal, texcoord;
+};
+
+// nodes.py:107-111 + common.py:140-149; the +1 texel is clamped (reference reads one past
+// the end with weight 0 there)
+__device__ V3 tex_sample(const float *__restrict__ tex, int w, int h, int c, float u, float v) {
+    float p0 = u * (float)(w - 1), p1 = v * (float)(h - 1);
+    int I0 = f2i(floorf(p0)), I1 = f2i(floorf(p1));
+    float x0 = p0 - (float)I0, x1 = p1 - (float)I1;
+    float y0 = 1.0f - x0, y1 = 1.0f - x1;
+    int i0 = min(max(I0, 0), w - 1), j0 = min(max(I1, 0), h - 1);
+    int i1 = min(max(I0 + 1, 0), w - 1), j1 = min(max(I1 + 1, 0), h - 1);
+    float o[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        int kk = c == 1 ? 0 : k;
+        float f11 = __ldg(tex + ((long long)i1 * h + j1) * c + kk);
+        float f10 = __ldg(tex + ((long long)i1 * h + j0) * c + kk);
+        float f00 = __ldg(tex + ((long long)i0 * h + j0) * c + kk);
+        float f01 = __ldg(tex + ((long long)i0 * h + j1) * c + kk);
+        o[k] = ((f11 * x0 * x1 + f10 * x0 * y1) + f00 * y0 * y1) + f01 * y0 * x1;
+    }
+    return v3(o[0], o[1], o[2]);
+}
+
+// ---- material ops shared by the VM and the specialised paths (same op order => same bits) ----
+template <bool FAST = false>
+__device__ __forceinline__ V3 op_phong(V3 mm, V3 nrm, V3 idir, V3 odir) { // material.py:450-454, common.py:197-199
+    V3 I3 = v3(-idir.x, -idir.y, -idir.z);
+    if (FAST) {
+        const float t = 2.0f * fdot3(nrm, I3);
+        V3 rdir = v3(fmaf(-t, nrm.x, I3.x), fmaf(-t, nrm.y, I3.y), fmaf(-t, nrm.z, I3.z));
+        const float VoR = fmaxf(0.0f, fdot3(odir, rdir));
+        const float m = mm.x;
+        if (mm.x == mm.y && mm.x == mm.z && m >= 1.0f && m <= 1024.0f && m == truncf(m)) {
+            // integer shineness (uniform over the launch): square-and-multiply, <= 2*log2(m) roundings
+            const int e = (int)m;
+            float r = (e & 1) ? VoR : 1.0f, b = VoR;
+#pragma unroll
+            for (int k = 1; k <= 10; k++) {
+                if ((e >> k) == 0) break;
+                b *= b;
+                if ((e >> k) & 1) r *= b;
+            }
+            r *= fmaf(m, 0.5f, 1.0f);
+            return v3(r, r, r);
+        }
+    }
+    float t = 2.0f * dot3(nrm, I3);
+    V3 rdir = v3(I3.x - t * nrm.x, I3.y - t * nrm.y, I3.z - t * nrm.z);
+    float VoR = fmaxf(0.0f, dot3(odir, rdir));
+    if (mm.x == mm.y && mm.x == mm.z) { // scalar shineness (the usual case): one powf
+        float r = powf(VoR, mm.x) * (mm.x + 2.0f) / 2.0f;
+        return v3(r, r, r);
+    }
+    return v3(powf(VoR, mm.x) * (mm.x + 2.0f) / 2.0f, powf(VoR, mm.y) * (mm.y + 2.0f) / 2.0f,
+              powf(VoR, mm.z) * (mm.z + 2.0f) / 2.0f);
+}
+__device__ __forceinline__ V3 op_cook(V3 ro, V3 f0, V3 nrm, V3 idir, V3 odir) { // material.py:323-362
+    const float EPS = 1e-10f, eps = 1e-6f;
+    V3 half = normalized(v3(idir.x + odir.x, idir.y + odir.y, idir.z + odir.z));
+    float NoH = fmaxf(EPS, dot3(half, nrm));
+    float NoL = fmaxf(EPS, dot3(idir, nrm));
+    float NoV = fmaxf(EPS, dot3(odir, nrm));
+    float VoH = fminf(1.0f, fmaxf(EPS, dot3(half, odir))); // 1 - 1e-10 == 1.0f
+    float fr = powf(1.0f - VoH, 5.0f);
+    float rr[3] = {ro.x, ro.y, ro.z}, ff[3] = {f0.x, f0.y, f0.z}, o[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        float alpha2 = fmaxf(eps, rr[k] * rr[k]);
+        float denom = 1.0f - (NoH * NoH) * (1.0f - alpha2);
+        float ndf = alpha2 / (denom * denom);
+        float kk = alpha2 / 2.0f;
+        float vdf = 1.0f / ((NoV * kk + 1.0f) - kk);
+        vdf *= 1.0f / ((NoL * kk + 1.0f) - kk);
+        vdf /= 1.0f * (1.0f - alpha2) + 12.566370614359172f * alpha2; // common.py:221-223 lerp(alpha2, 1, 4 pi)
+        float fdf = ff[k] + (1.0f - ff[k]) * fr;
+        o[k] = fdf * vdf * ndf;
+    }
+    return v3(o[0], o[1], o[2]);
+}
+__device__ __forceinline__ V3 op_mix(V3 f, V3 a, V3 b) { // material.py:96-118
+    return v3((1.0f - f.x) * a.x + f.x * b.x, (1.0f - f.y) * a.y + f.y * b.y, (1.0f - f.z) * a.z + f.z * b.z);
+}
+__device__ __forceinline__ V3 op_mix_fast(V3 f, V3 a, V3 b) {
+    return v3(fmaf(f.x, b.x, (1.0f - f.x) * a.x), fmaf(f.y, b.y, (1.0f - f.y) * a.y), fmaf(f.z, b.z, (1.0f - f.z) * a.z));
+}
+
+#define STK 12
+__device__ V3 run_program(const TinaMaterial &m, int begin, int n, const ShadeIn &in, V3 nrm, V3 idir, V3 odir, V3 *regs) {
+    V3 st[STK];
+    int sp = 0;
+    for (int pc = begin; pc < begin + n; pc++) {
+        const TinaInstr &I = m.code[pc];
+        switch (I.op) {
+        case TINA_OP_REG:
+            st[sp++] = regs[I.arg & (TINA_MAX_REGS - 1)];
+            break;
+        case TINA_OP_STORE:
+            regs[I.arg & (TINA_MAX_REGS - 1)] = st[--sp];
+            break;
+        case TINA_OP_CONST:
+            st[sp++] = v3(I.c[0], I.c[1], I.c[2]);
+            break;
+        case TINA_OP_INPUT:
+            st[sp++] = I.arg == 0 ? in.pos : I.arg == 1 ? in.color : I.arg == 2 ? in.normal : in.texcoord;
+            break;
+        case TINA_OP_TEXTURE: {
+            V3 uv = st[sp - 1];
+            st[sp - 1] = tex_sample(m.tex[I.arg], m.tex_w[I.arg], m.tex_h[I.arg], m.tex_c[I.arg], uv.x, uv.y);
+            break;
+        }
+        case TINA_OP_FRESNEL: { // material.py:69-83
+            V3 sp_ = st[sp - 1], al = st[sp - 2], me = st[sp - 3];
+            V3 r;
+            r.x = me.x * al.x + (1.0f - me.x) * 0.16f * (sp_.x * sp_.x);
+            r.y = me.y * al.y + (1.0f - me.y) * 0.16f * (sp_.y * sp_.y);
+            r.z = me.z * al.z + (1.0f - me.z) * 0.16f * (sp_.z * sp_.z);
+            sp -= 2;
+            st[sp - 1] = r;
+            break;
+        }
+        case TINA_OP_LAMBERT: { // material.py:392-393
+            const float v = 0.3183098861837907f;
+            st[sp++] = v3(v, v, v);
+            break;
+        }
+        case TINA_OP_PHONG:
+            st[sp - 1] = op_phong(st[sp - 1], nrm, idir, odir);
+            break;
+        case TINA_OP_COOK: {
+            V3 f0 = st[sp - 1], ro = st[sp - 2];
+            sp -= 1;
+            st[sp - 1] = op_cook(ro, f0, nrm, idir, odir);
+            break;
+        }
+        case TINA_OP_MIX: {
+            V3 b = st[sp - 1], a = st[sp - 2], f = st[sp - 3];
+            sp -= 2;
+            st[sp - 1] = op_mix(f, a, b);
+            break;
+        }
+        case TINA_OP_MUL: { // material.py:157-176
+            V3 w = st[sp - 1], f = st[sp - 2];
+            sp -= 1;
+            st[sp - 1] = v3(f.x * w.x, f.y * w.y, f.z * w.z);
+            break;
+        }
+        case TINA_OP_ADD: {
+            V3 b = st[sp - 1], a = st[sp - 2];
+            sp -= 1;
+            st[sp - 1] = v3(a.x + b.x, a.y + b.y, a.z + b.z);
+            break;
+        }
+        default:
+            break;
+        }
+    }
+    return sp > 0 ? st[sp - 1] : v3(0.f, 0.f, 0.f);
+}
+
+// operand i of a specialised brdf shape: a constant or a prologue register
+__device__ __forceinline__ V3 operand(const TinaMaterial &m, int i, const V3 *regs) {
+    if (m.code[i].op == TINA_OP_REG) return regs[m.code[i].arg & (TINA_MAX_REGS - 1)];
+    return v3(m.code[i].c[0], m.code[i].c[1], m.code[i].c[2]);
+}
+// a program that the host folded down to one constant / one register needs no interpreter
+__device__ __forceinline__ V3 run_or_const(const TinaMaterial &m, int begin, int n, const ShadeIn &in, V3 *regs) {
+    if (n == 1 && (m.code[begin].op == TINA_OP_CONST || m.code[begin].op == TINA_OP_REG)) return operand(m, begin, regs);
+    const V3 zero = v3(0.f, 0.f, 0.f);
+    return run_program(m, begin, n, in, zero, zero, zero, regs);
+}
+
+__device__ __forceinline__ float aces(float c) { // advans.py:32-35
+    return c * (2.51f * c + 0.03f) / (c * (2.43f * c + 0.59f) + 0.14f);
+}
+template <bool FAST>
+__device__ __forceinline__ float aces_t(float c) {
+    if (!FAST) return aces(c);
+    return c * fmaf(2.51f, c, 0.03f) * rcp_fast(fmaf(c, fmaf(2.43f, c, 0.59f), 0.14f));
+}
+
+// the part of triangle.py:93-113 that render_color re-reads from the setup cache (:140-145):
+// b, c, bcn, can, wscale.  Same ops as setup_face for these values => same bits.
+__device__ __forceinline__ void setup_weights_clip(float4 ca, float4 cb, float4 cc, const Cam &cam, Setup &s) {
+    const float ax = ca.x, ay = ca.y, aw = ca.w, bx = cb.x, by = cb.y, bw = cb.w, cx = cc.x, cy = cc.y, cw = cc.w;
+    const float rx = cam.fW, ry = cam.fH;
+    float pax = fm(fa(fm(ax, 0.5f), 0.5f), rx), pay = fm(fa(fm(ay, 0.5f), 0.5f), ry);
+    float pbx = fm(fa(fm(bx, 0.5f), 0.5f), rx), pby = fm(fa(fm(by, 0.5f), 0.5f), ry);
+    float pcx = fm(fa(fm(cx, 0.5f), 0.5f), rx), pcy = fm(fa(fm(cy, 0.5f), 0.5f), ry);
+    float n = fs(fm(fs(pbx, pax), fs(pcy, pay)), fm(fs(pby, pay), fs(pcx, pax)));
+    {
+        const float a[4] = {fs(pbx, pcx), fs(pby, pcy), fs(pcx, pax), fs(pcy, pay)};
+        float q[4];
+        div_many(a, n, q);
+        s.bcnx = q[0], s.bcny = q[1], s.canx = q[2], s.cany = q[3];
+    }
+    s.bx = pbx, s.by = pby, s.cx = pcx, s.cy = pcy;
+    s.w0 = fd(1.0f, aw), s.w1 = fd(1.0f, bw), s.w2 = fd(1.0f, cw);
+}
+__device__ __forceinline__ void setup_weights(const float *v, const Cam &cam, Setup &s) {
+    setup_weights_clip(vertex_clip(cam, v[0], v[1], v[2]), vertex_clip(cam, v[3], v[4], v[5]), vertex_clip(cam, v[6], v[7], v[8]),
+                       cam, s);
+}
+
+// brdf program shapes the host's constant folding produces for the stock materials
+#define MAT_GENERIC 0 /* interpret the program                                             */
+#define MAT_CONST 1   /* [X]                      tina.Diffuse (X = CONST or a prologue REGister) */
+#define MAT_CLASSIC 2 /* [X f, X a, X m, PHONG, MIX]                  tina.Classic        */
+#define MAT_PBR 3     /* [X f, X a, X ro, X f0, COOK, MIX]            tina.PBR            */
+
+// shade one covered pixel: triangle.py:139-153 + :32-49 + shader.py:119-131 + lighting.py:84-98
+// triangle.py:139-153 + :32-49: gather face f, recompute the weights at pixel P, interpolate
+// CF >= 0: the raster's SMOOTHING / TEXTURING bits as a compile-time constant (lean kernels), else runtime `flags_rt`
+template <bool IDX, bool FAST = false, int CF = -1, int CK = 0>
+__device__ __forceinline__ void pixel_inputs(int P, unsigned f, const float *__restrict__ verts, const float *__restrict__ norms,
+                                             const float *__restrict__ coors, const Cam &cam, uint32_t flags_rt, const Src &S,
+                                             ShadeIn &in, float &px, float &py) {
+    const uint32_t flags = CF >= 0 ? (uint32_t)CF : flags_rt;
+    const int x = P / cam.H, y = P - x * cam.H;
+    float vv[9], n9[9], t6[6];
+    Setup s;
+    bool nsign = false;
+    if (IDX) { // gather the face's corners through the mesh's own indexing (per-unique-vertex arrays)
+        int iv[3], it[3], in_[3], gi[3], gj[3];
+        bool neg;
+        corner_ids<CK>(S, (long long)f, iv, it, in_, gi, gj, neg);
+        // every gather is issued before the first use of any of them (one exposed round trip, not three);
+        // the sign of a negated normal is applied after the interpolation (-(x) commutes with rounding)
+        const float4 ca = __ldg(S.vclip + iv[0]), cb = __ldg(S.vclip + iv[1]), cc = __ldg(S.vclip + iv[2]);
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const float *p = S.vpos + (long long)iv[k] * 3;
+            vv[k * 3] = __ldg(p), vv[k * 3 + 1] = __ldg(p + 1), vv[k * 3 + 2] = __ldg(p + 2);
+        }
+        if (flags & TINA_SMOOTHING) {
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const float *p = S.vnrm + (long long)in_[k] * 3;
+                n9[k * 3] = __ldg(p), n9[k * 3 + 1] = __ldg(p + 1), n9[k * 3 + 2] = __ldg(p + 2);
+            }
+            nsign = neg;
+        }
+        if (flags & TINA_TEXTURING) {
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                if (S.kind == 1) { // grid.py:17-21: I / (res - 1)
+                    t6[k * 2] = (float)gi[k] / (float)(S.nx - 1), t6[k * 2 + 1] = (float)gj[k] / (float)(S.ny - 1);
+                } else {
+                    const float *p = S.vtex + (long long)it[k] * 2;
+                    t6[k * 2] = __ldg(p), t6[k * 2 + 1] = __ldg(p + 1);
+                }
+            }
+        }
+        setup_weights_clip(ca, cb, cc, cam, s);
+    } else {
+        const float *v = verts + (long long)f * 9;
+#pragma unroll
+        for (int k = 0; k < 9; k++) vv[k] = __ldg(v + k);
+        if (flags & TINA_SMOOTHING) {
+            const float *nn = norms + (long long)f * 9;
+#pragma unroll
+            for (int k = 0; k < 9; k++) n9[k] = __ldg(nn + k);
+        }
+        if (flags & TINA_TEXTURING) {
+            const float *tt = coors + (long long)f * 6;
+#pragma unroll
+            for (int k = 0; k < 6; k++) t6[k] = __ldg(tt + k);
+        }
+        setup_weights(vv, cam, s);
+    }
+    px = fa((float)x, cam.bias[0]), py = fa((float)y, cam.bias[1]);
+    PW w = pix_products(s, px, py);
+    float q0, q1, q2;
+    pix_finish(s, w, q0, q1, q2);
+    // triangle.py:32-49 interpolate
+    if (FAST) {
+        in.pos = v3(fmaf(q2, vv[6], fmaf(q1, vv[3], q0 * vv[0])), fmaf(q2, vv[7], fmaf(q1, vv[4], q0 * vv[1])),
+                    fmaf(q2, vv[8], fmaf(q1, vv[5], q0 * vv[2])));
+        if (flags & TINA_SMOOTHING)
+            in.normal = v3(fmaf(q2, n9[6], fmaf(q1, n9[3], q0 * n9[0])), fmaf(q2, n9[7], fmaf(q1, n9[4], q0 * n9[1])),
+                           fmaf(q2, n9[8], fmaf(q1, n9[5], q0 * n9[2])));
+    } else {
+        in.pos = v3((q0 * vv[0] + q1 * vv[3]) + q2 * vv[6], (q0 * vv[1] + q1 * vv[4]) + q2 * vv[7],
+                    (q0 * vv[2] + q1 * vv[5]) + q2 * vv[8]);
+        if (flags & TINA_SMOOTHING)
+            in.normal = v3((q0 * n9[0] + q1 * n9[3]) + q2 * n9[6], (q0 * n9[1] + q1 * n9[4]) + q2 * n9[7],
+                           (q0 * n9[2] + q1 * n9[5]) + q2 * n9[8]);
+    }
+    if (nsign) in.normal = v3(-in.normal.x, -in.normal.y, -in.normal.z);
+    if (!(flags & TINA_SMOOTHING))
+        in.normal = cross3(v3(vv[3] - vv[0], vv[4] - vv[1], vv[5] - vv[2]), v3(vv[6] - vv[0], vv[7] - vv[1], vv[8] - vv[2]));
+    in.normal = normalized_t<FAST>(in.normal);
+    in.texcoord = v3(0.f, 0.f, 0.f);
+    if (flags & TINA_TEXTURING) {
+        in.texcoord.x = (q0 * t6[0] + q1 * t6[2]) + q2 * t6[4];
+        in.texcoord.y = (q0 * t6[1] + q1 * t6[3]) + q2 * t6[5];
+    }
+    in.color = v3(1.f, 1.f, 1.f);
+}
+
+// shader.py:82-93 calc_viewdir
+template <bool FAST = false>
+__device__ __forceinline__ V3 view_direction(const Cam &cam, float px, float py) {
+    if (FAST) {
+        // same ray without the six divisions: with h0 = V2W (qx,qy,-1,1), h1 = V2W (qx,qy,+1,1) the reference's
+        // ro1 - ro = h1.xyz/h1.w - h0.xyz/h0.w is parallel to h1.xyz*h0.w - h0.xyz*h1.w (sign of h0.w*h1.w)
+        const float *V = cam.V2W;
+        const float qx = fmaf(px, cam.inv2W, -1.0f), qy = fmaf(py, cam.inv2H, -1.0f);
+        const float b0 = fmaf(V[0], qx, fmaf(V[1], qy, V[3])), b1 = fmaf(V[4], qx, fmaf(V[5], qy, V[7]));
+        const float b2 = fmaf(V[8], qx, fmaf(V[9], qy, V[11])), b3 = fmaf(V[12], qx, fmaf(V[13], qy, V[15]));
+        const float w0 = b3 - V[14], w1 = b3 + V[14];
+        V3 d = v3(fmaf(b0 + V[2], w0, -(b0 - V[2]) * w1), fmaf(b1 + V[6], w0, -(b1 - V[6]) * w1),
+                  fmaf(b2 + V[10], w0, -(b2 - V[10]) * w1));
+        float inv = rsq_fast(fdot3(d, d));
+        if (w0 * w1 > 0.0f) inv = -inv; // returns -rd
+        return v3(d.x * inv, d.y * inv, d.z * inv);
+    }
+    const float qx = px / cam.fW * 2.0f - 1.0f, qy = py / cam.fH * 2.0f - 1.0f;
+    V3 ro = mapply_pos3(cam.V2W, qx, qy, -1.0f), ro1 = mapply_pos3(cam.V2W, qx, qy, 1.0f);
+    V3 rd = normalized(v3(ro1.x - ro.x, ro1.y - ro.y, ro1.z - ro.z));
+    return v3(-rd.x, -rd.y, -rd.z);
+}
+
+// lighting.py:84-98 (+ the per-pixel prologue registers of the material program)
+// LEANOPS: the host verified that the material has no prologue and that every operand of the brdf shape, the
+// ambient and the emission program is a constant (or absent): no register file, no interpreter, no operand tests.
+__device__ __forceinline__ V3 const_operand(const TinaMaterial &m, int i) { return v3(m.code[i].c[0], m.code[i].c[1], m.code[i].c[2]); }
+template <int KIND, bool FAST = false, bool LEANOPS = false>
+__device__ __forceinline__ V3 light_pixel(const ShadeIn &in, V3 viewdir, const TinaMaterial &mat, const TinaLighting &L) {
+    V3 res = v3(0.f, 0.f, 0.f);
+    V3 regs[LEANOPS ? 1 : TINA_MAX_REGS];
+    if (LEANOPS) {
+        if (mat.n_emission) res = const_operand(mat, mat.n_brdf + mat.n_ambient);
+        if (mat.n_ambient) {
+            const V3 am = const_operand(mat, mat.n_brdf);
+            res.x += L.ambient[0] * am.x, res.y += L.ambient[1] * am.y, res.z += L.ambient[2] * am.z;
+        }
+    } else {
+        if (mat.n_prologue) { // light-independent sub-expressions (texture samples, Fresnel factors ...), once per pixel
+            const V3 zero = v3(0.f, 0.f, 0.f);
+            run_program(mat, mat.n_brdf + mat.n_ambient + mat.n_emission, mat.n_prologue, in, zero, zero, zero, regs);
+        }
+        V3 em = run_or_const(mat, mat.n_brdf + mat.n_ambient, mat.n_emission, in, regs);
+        res.x += em.x, res.y += em.y, res.z += em.z;
+        V3 am = run_or_const(mat, mat.n_brdf, mat.n_ambient, in, regs);
+        res.x += L.ambient[0] * am.x, res.y += L.ambient[1] * am.y, res.z += L.ambient[2] * am.z;
+    }
+    for (int l = 0; l < L.nlights; l++) {
+        const float lw = L.dirs[l][3];
+        V3 ld = v3(L.dirs[l][0] - in.pos.x * lw, L.dirs[l][1] - in.pos.y * lw, L.dirs[l][2] - in.pos.z * lw);
+        float cos_i, d2;
+        if (FAST) {
+            d2 = fdot3(ld, ld);
+            const float inv = rsq_fast(d2);
+            ld = v3(ld.x * inv, ld.y * inv, ld.z * inv);
+            cos_i = fdot3(in.normal, ld);
+        } else {
+            float dist = sqrtf(dot3(ld, ld));
+            ld = v3(ld.x / dist, ld.y / dist, ld.z / dist);
+            cos_i = dot3(in.normal, ld);
+            d2 = dist * dist;
+        }
+        if (cos_i > 0.0f) {
+            V3 mc;
+            if (LEANOPS && KIND == MAT_CONST) {
+                mc = const_operand(mat, 0);
+            } else if (LEANOPS && KIND == MAT_CLASSIC) {
+                V3 ph = op_phong<FAST>(const_operand(mat, 2), in.normal, ld, viewdir);
+                mc = FAST ? op_mix_fast(const_operand(mat, 0), const_operand(mat, 1), ph)
+                          : op_mix(const_operand(mat, 0), const_operand(mat, 1), ph);
+            } else if (KIND == MAT_CONST) {
+                mc = operand(mat, 0, regs);
+            } else if (KIND == MAT_CLASSIC) {
+                V3 ph = op_phong<FAST>(operand(mat, 2, regs), in.normal, ld, viewdir);
+                mc = FAST ? op_mix_fast(operand(mat, 0, regs), operand(mat, 1, regs), ph)
+                          : op_mix(operand(mat, 0, regs), operand(mat, 1, regs), ph);
+            } else if (KIND == MAT_PBR) {
+                V3 ck = op_cook(operand(mat, 2, regs), operand(mat, 3, regs), in.normal, ld, viewdir);
+                mc = op_mix(operand(mat, 0, regs), operand(mat, 1, regs), ck);
+            } else {
+                mc = run_program(mat, 0, mat.n_brdf, in, in.normal, ld, viewdir, regs);
+            }
+            if (FAST) {
+                const float k = cos_i * rcp_fast(d2);
+                res.x = fmaf(k * L.colors[l][0], mc.x, res.x);
+                res.y = fmaf(k * L.colors[l][1], mc.y, res.y);
+                res.z = fmaf(k * L.colors[l][2], mc.z, res.z);
+            } else {
+                res.x += cos_i * (L.colors[l][0] / d2) * mc.x;
+                res.y += cos_i * (L.colors[l][1] / d2) * mc.y;
+                res.z += cos_i * (L.colors[l][2] / d2) * mc.z;
+            }
+        }
+    }
+    return res;
+}
+
+// shade one covered pixel: shader.py:119-131 + lighting.py:84-98
+// LEAN: 0 generic; else a lean kernel for rasters without texturing (compile-time flags, constant operands):
+// 1 / 2 = flat / smooth with the source kind read at run time; 3 / 4 = flat / smooth on a plain MeshGrid source,
+// 5 / 6 = on a plain MeshModel source (indexed, mode 0: corner_ids with compile-time kind)
+template <int KIND, bool IDX, bool FAST, int LEAN = 0>
+__device__ __forceinline__ V3 shade_pixel(int P, unsigned f, const float *__restrict__ verts, const float *__restrict__ norms,
+                                       const float *__restrict__ coors, const Cam &cam, uint32_t flags,
+                                       const TinaMaterial &mat, const TinaLighting &L, const Src &S) {
+    ShadeIn in;
+    float px, py;
+    pixel_inputs<IDX, FAST, LEAN == 0 ? -1 : ((LEAN & 1) ? 0 : (int)TINA_SMOOTHING), LEAN <= 2 ? 0 : (LEAN <= 4 ? 1 : 2)>(
+        P, f, verts, norms, coors, cam, flags, S, in, px, py);
+    return light_pixel<KIND, FAST, LEAN != 0>(in, view_direction<FAST>(cam, px, py), mat, L);
+}
+
+// K4: one CTA per 256-pixel chunk, one thread per pixel (x-major, so a warp covers 32 consecutive y).
+// Measured alternatives on C2 (profiles/r1_k4_variants.md): 4 pixels per thread with serial shading 62 us,
+// 4-pixel classification + shared-memory compaction + CTA-wide shading 37 us, persistent CTAs striding over
+// chunks (flags read in one batch, next key prefetched) 25.0 us, persistent warps over 32-pixel units 25-27 us,
+// this mapping 25 us (29-31 us before the relaxed shading arithmetic).
+#ifndef K4_THREADS
+#define K4_THREADS 256
+#endif
+#ifndef K4_MINBLOCKS
+#define K4_MINBLOCKS 4
+#endif
+// key buffers of all ranks for the fused composite (n == 0: plain render_color on the local keys)
+struct PeerTab {
+    const long long *p[TINA_MAX_PEERS];
+    int n, self;
+};
+
+template <int KIND, bool IDX, bool FAST, int LEAN = 0>
+__global__ void __launch_bounds__(K4_THREADS, K4_MINBLOCKS)
+k_render_color(const long long *__restrict__ keys, const float *__restrict__ verts, const float *__restrict__ norms,
+               const float *__restrict__ coors, const __grid_constant__ Cam cam, uint32_t flags, unsigned base,
+               unsigned nfaces, const __grid_constant__ TinaMaterial mat, const __grid_constant__ TinaLighting L,
+               float *__restrict__ image, uint32_t cflags, float bg0, float bg1, float bg2,
+               const __grid_constant__ Src S, const unsigned char *__restrict__ blkflags, unsigned *__restrict__ publish,
+               const unsigned *__restrict__ counters, int pix_lo, int pix_hi, unsigned *__restrict__ pubstate,
+               unsigned char flagval, const __grid_constant__ PeerTab peers, long long *__restrict__ keys_out) {
+    static_assert(K4_THREADS == (1 << FLAG_SHIFT), "one coverage flag per K4 block");
+    pdl_wait();
+    if (blockIdx.x == 0 && threadIdx.x == 0 && publish) { // tell the host how many faces needed the tile path
+        // running counts live in device memory; the mapped host words are only written (posted stores, no PCIe
+        // round trip).  The host reads them as a heuristic, a stale value is harmless.
+        const unsigned nq = counters[0];
+        const unsigned npub = pubstate[0] + 1u;              // publishes so far
+        const unsigned streak = nq ? 0u : pubstate[1] + 1u;  // consecutive render_occup/render_color pairs without large faces
+        pubstate[0] = npub, pubstate[1] = streak;
+        publish[0] = nq, publish[1] = npub, publish[2] = streak;
+    }
+    const int npix = pix_hi; // this launch shades pixels [pix_lo, pix_hi); pix_lo is a multiple of 256
+    const bool fill = (cflags & TINA_COLOR_FILL_BG) != 0;
+    float r = bg0, g = bg1, b = bg2;
+    if (fill && (cflags & TINA_COLOR_TONEMAP)) r = aces(r), g = aces(g), b = aces(b);
+    const long long p0 = (long long)pix_lo + ((long long)blockIdx.x << FLAG_SHIFT);
+    // flagval != 0: this object's render_occup was the engine's last, its flags carry its own stamp -> a chunk with
+    // any other value holds none of its pixels.  flagval == 0: only "nothing rasterised here since the clear" is known.
+    const unsigned char cf = blkflags ? blkflags[(pix_lo >> FLAG_SHIFT) + blockIdx.x] : (unsigned char)1;
+    if (blkflags && (flagval ? cf != flagval : cf == 0)) {
+        if (fill) {
+            const int np = (int)min((long long)K4_THREADS, (long long)npix - p0);
+            const int t = threadIdx.x;
+            if (np == K4_THREADS && (((uintptr_t)image) & 15) == 0) { // 3072 contiguous, 16-byte aligned bytes: 192 float4 stores
+                if (t < 192) {
+                    const int m = t % 3;
+                    const float4 v = m == 0 ? make_float4(r, g, b, r) : m == 1 ? make_float4(g, b, r, g) : make_float4(b, r, g, b);
+                    __stcs(reinterpret_cast<float4 *>(image + p0 * 3) + t, v);
+                }
+            } else if (t < np) {
+                float *out = image + (p0 + t) * 3;
+                out[0] = r, out[1] = g, out[2] = b;
+            }
+        }
+        return;
+    }
+    const long long Pl = p0 + threadIdx.x;
+    if (Pl >= npix) return;
+    const int P = (int)Pl;
+    unsigned id;
+    if (peers.n > 1) {
+        // sort-last composite fused into the shading pass: the winner of this pixel is the MIN of the packed keys
+        // of every rank, read straight from the peers' key buffers over NVLink (L2-coherent loads: a peer's buffer
+        // changes between frames, L1 must not keep it); the composited key is kept in the local buffer
+        long long k = __ldcg(peers.p[0] + P);
+#pragma unroll 1
+        for (int q = 1; q < peers.n; q++) {
+            const long long o = __ldcg(peers.p[q] + P);
+            k = o < k ? o : k;
+        }
+        keys_out[P] = k;
+        id = (unsigned)(unsigned long long)k;
+    } else {
+        id = (unsigned)(unsigned long long)__ldcs(keys + P);
+    }
+    const unsigned fid = id - 1u - base;
+    float *out = image + (long long)P * 3;
+    if (id == 0u || fid >= nfaces) { // triangle.py:137-138 (occup == -1)
+        if (fill) __stcs(out, r), __stcs(out + 1, g), __stcs(out + 2, b);
+        return;
+    }
+    V3 c = shade_pixel<KIND, IDX, FAST, LEAN>(P, fid, verts, norms, coors, cam, flags, mat, L, S);
+    if (cflags & TINA_COLOR_TONEMAP) c.x = aces_t<FAST>(c.x), c.y = aces_t<FAST>(c.y), c.z = aces_t<FAST>(c.z);
+    __stcs(out, c.x), __stcs(out + 1, c.y), __stcs(out + 2, c.z);
+}
+
+// G-buffer sinks (core/shader.py:21-109): one attribute of the visible surface per pixel
+template <bool IDX>
+__global__ void __launch_bounds__(256)
+k_gbuffer(const long long *__restrict__ keys, const float *__restrict__ verts, const float *__restrict__ norms,
+          const float *__restrict__ coors, const __grid_constant__ Cam cam, uint32_t flags, unsigned base, unsigned nfaces,
+          int kind, void *__restrict__ outp, int ncomp, int out_is_int, float p0, float p1, float p2,
+          const __grid_constant__ Src S) {
+    pdl_wait();
+    const int P = blockIdx.x * blockDim.x + threadIdx.x;
+    if (P >= cam.W * cam.H) return;
+    const long long key = keys[P];
+    const unsigned id = (unsigned)(unsigned long long)key;
+    const unsigned f = id - 1u - base;
+    if (id == 0u || f >= nfaces) return; // triangle.py:137-138: sinks are only written where this object is visible
+    float v[3] = {0.f, 0.f, 0.f};
+    if (kind == TINA_SINK_CONST) {
+        v[0] = p0, v[1] = p1, v[2] = p2;
+    } else if (kind == TINA_SINK_DEPTH) {
+        v[0] = v[1] = v[2] = (float)(int)(key >> 32); // shader.py:39-42: engine.depth[P]
+    } else if (kind == TINA_SINK_COLOR) {
+        v[0] = v[1] = v[2] = 1.0f; // triangle.py:48
+    } else {
+        ShadeIn in;
+        float px, py;
+        pixel_inputs<IDX>(P, f, verts, norms, coors, cam, flags, S, in, px, py);
+        if (kind == TINA_SINK_POSITION) {
+            v[0] = in.pos.x, v[1] = in.pos.y, v[2] = in.pos.z;
+        } else if (kind == TINA_SINK_NORMAL) {
+            v[0] = in.normal.x, v[1] = in.normal.y, v[2] = in.normal.z;
+        } else if (kind == TINA_SINK_VIEWNORMAL) { // shader.py:51-58: mapply_dir(W2V, normal).normalized()
+            float r0, r1, r2, rw;
+            mapply(cam.W2V, in.normal.x, in.normal.y, in.normal.z, 0.0f, r0, r1, r2, rw);
+            V3 n = normalized(v3(r0, r1, r2));
+            v[0] = n.x, v[1] = n.y, v[2] = n.z;
+        } else if (kind == TINA_SINK_TEXCOORD) {
+            v[0] = in.texcoord.x, v[1] = in.texcoord.y;
+        } else if (kind == TINA_SINK_CHESSBOARD) { // shader.py:73-79: lerp((p // size).sum() % 2, 0.4, 0.9)
+            const float fac = fmodf(floorf(px / p0) + floorf(py / p0), 2.0f);
+            const float m = fac < 0.0f ? fac + 2.0f : fac; // python-style modulo
+            v[0] = v[1] = v[2] = 0.4f * (1.0f - m) + 0.9f * m;
+        } else {
+            const V3 vd = view_direction(cam, px, py);
+            if (kind == TINA_SINK_VIEWDIR) { // shader.py:96-101
+                v[0] = vd.x * 0.5f + 0.5f, v[1] = vd.y * 0.5f + 0.5f, v[2] = vd.z * 0.5f + 0.5f;
+            } else { // TINA_SINK_SIMPLE, shader.py:104-109
+                v[0] = v[1] = v[2] = fabsf(dot3(in.normal, vd));
+            }
+        }
+    }
+    if (out_is_int) {
+        int *o = reinterpret_cast<int *>(outp) + (long long)P * ncomp;
+        for (int k = 0; k < ncomp; k++) o[k] = (int)v[k];
+    } else {
+        float *o = reinterpret_cast<float *>(outp) + (long long)P * ncomp;
+        for (int k = 0; k < ncomp; k++) o[k] = v[k];
+    }
+}

@@ -146,7 +146,10 @@ def test_product_never_imports_oracle():
     for fn in os.listdir(pkg):
         if fn.endswith('.py'):
             assert 'oracle' not in open(os.path.join(pkg, fn)).read(), fn
-    assert 'oracle' not in open(os.path.join(pkg, 'csrc', 'tina_b200.cu')).read().replace('the serial CPU restatement', '')
+    csrc = os.path.join(pkg, 'csrc')
+    for fn in os.listdir(csrc):
+        if fn.endswith(('.cu', '.cuh')):
+            assert 'oracle' not in open(os.path.join(csrc, fn)).read().replace('the serial CPU restatement', ''), fn
 
 
 def test_material_compile_shapes(tina):

@@ -907,7 +907,7 @@ def test_peer_memory_composite_equals_single_engine(tina, O):
 
 def test_shared_divisor_division_is_ieee(tina):
     """The setup code divides several numbers by one divisor with the reciprocal refinement shared (div_many in
-    tina_b200.cu); it must return the bits of IEEE round-to-nearest division for every operand: 6e9 quotients
+    csrc/common.cuh); it must return the bits of IEEE round-to-nearest division for every operand: 6e9 quotients
     (random bit patterns incl. nan / inf / denormals, moderate exponents with random mantissas, quotients at and next to 1,
     signed zeros, all-ones mantissas, reciprocals) against __fdiv_rn."""
     import ctypes as C
