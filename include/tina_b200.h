@@ -272,6 +272,13 @@ int tina_wire_render_color(TinaWire *w, float *const *images_host, int nimages, 
 /* ---- frame glue (scene/raster.py:176,202-203) -------------------------------- */
 int tina_image_fill(float *image, int64_t npixels, const float *rgb_host, void *stream);
 int tina_image_tonemap(float *image, int64_t nfloats, void *stream);
+/* SSAO (postp/ssao.py, non-TAA mode).  render (:65-96): ambient-occlusion field ao [W,H] from the engine's depth, the
+ * scene's world-normal G-buffer normals [W,H,3] (NormalShader, scene/raster.py:51-54), the sample table [nsamples,3] and
+ * the rotation table [noise_size,noise_size,2] that the reference draws once at construction (:24-36).
+ * apply (:38-49): image [W,H,3] *= 1 - box_{noise_size}(ao) / noise_size^2. */
+int tina_engine_ssao_render(TinaEngine *e, const float *normals, const float *samples, int nsamples, const float *rotations,
+                            int noise_size, float radius, float thresh, float factor, float *ao, void *stream);
+int tina_image_ssao_apply(float *image, const float *ao, int W, int H, int noise_size, void *stream);
 /* FXAA (postp/fxaa.py:28-68) in place on image [W,H,3]; scratch_lumi [W*H], scratch_copy [W*H*3] floats.
  * Reference defaults: abs_thresh 0.0625, rel_thresh 0.063, factor 1.  Out-of-image taps read 0. */
 int tina_image_fxaa(float *image, int W, int H, float *scratch_lumi, float *scratch_copy, float abs_thresh,

@@ -176,6 +176,24 @@ def bloom(image, gwei, thresh=1.0, scale=0.25, factor=1.0):
     return out
 
 
+def ssao_render(depth, normals, W2V, V2W, samples, rotations, radius=0.2, thresh=0.0, factor=1.0, bias=(0.5, 0.5)):
+    depth = np.ascontiguousarray(depth, dtype=np.int32)
+    W, H = depth.shape
+    nrm, smp, rot = _f(normals), _f(samples), _f(rotations)
+    w2v, v2w, b = _f(W2V), _f(V2W), _f(bias)
+    ao = np.zeros((W, H), dtype=np.float32)
+    lib().orc_ssao_render(depth.ctypes.data_as(C.c_void_p), _p(nrm), _p(w2v), _p(v2w), _p(b), W, H, _p(smp), smp.shape[0], _p(rot),
+                          rot.shape[0], C.c_float(radius), C.c_float(thresh), C.c_float(factor), _p(ao))
+    return ao
+
+
+def ssao_apply(image, ao, noise_size=4):
+    out = np.ascontiguousarray(image, dtype=np.float32).copy()
+    a = _f(ao)
+    lib().orc_ssao_apply(_p(out), _p(a), out.shape[0], out.shape[1], int(noise_size))
+    return out
+
+
 def tonemap(image):
     out = np.ascontiguousarray(image, dtype=np.float32).copy()
     lib().orc_tonemap(_p(out), C.c_int64(out.size))

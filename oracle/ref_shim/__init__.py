@@ -101,10 +101,19 @@ class Matrix:
     def __call__(self, *idx):
         return self[idx if len(idx) > 1 else idx[0]]
 
-    x = property(lambda s: s[0], lambda s, v: s.__setitem__(0, v))
-    y = property(lambda s: s[1], lambda s, v: s.__setitem__(1, v))
-    z = property(lambda s: s[2], lambda s, v: s.__setitem__(2, v))
-    w = property(lambda s: s[3], lambda s, v: s.__setitem__(3, v))
+    def _set_component(self, i, v):
+        # `v = field[i]` in kernel scope is a COPY in Taichi (postp/ssao.py:84-88 then assigns v.x, v.y): a matrix
+        # handed out by Field.__getitem__ stays a live view only for subscript stores (field[None][2, 2] = -1 in
+        # Python scope, core/engine.py:24); component assignment detaches it first
+        if getattr(self, '_fview', False):
+            self.a = self.a.copy()
+            self._fview = False
+        self.__setitem__(i, v)
+
+    x = property(lambda s: s[0], lambda s, v: s._set_component(0, v))
+    y = property(lambda s: s[1], lambda s, v: s._set_component(1, v))
+    z = property(lambda s: s[2], lambda s, v: s._set_component(2, v))
+    w = property(lambda s: s[3], lambda s, v: s._set_component(3, v))
 
     def __repr__(self):
         return f'Matrix({self.a.tolist()})'
@@ -303,7 +312,9 @@ class Field:
             z = np.zeros(self.elem, dtype=self.dt)  # out-of-bounds read of a dense field
             return Matrix(z, _raw=True) if self.elem else z[()]
         if self.elem:
-            return Matrix(self.data[idx], _raw=True)  # live view: field[None][2, 2] = -1 works
+            m = Matrix(self.data[idx], _raw=True)  # live view: field[None][2, 2] = -1 works
+            m._fview = True
+            return m
         v = self.data[idx]
         return IntRef(v, self, idx) if self.dt == I32 else v
 
@@ -481,7 +492,7 @@ def make_transformations():
 
 NEEDED = ['common', 'advans', 'util.matrix', 'matr.nodes', 'matr.material', 'core.engine', 'core.lighting',
           'core.shader', 'core.triangle', 'mesh.base', 'mesh.simple', 'mesh.model', 'mesh.grid', 'mesh.trans',
-          'mesh.cull', 'mesh.norm', 'postp.tonemap', 'postp.fxaa', 'postp.blooming', 'assimp.obj', 'assimp.gltf', 'core.particle', 'core.wireframe', 'mesh.wire', 'pars.base',
+          'mesh.cull', 'mesh.norm', 'postp.tonemap', 'postp.fxaa', 'postp.blooming', 'postp.ssao', 'assimp.obj', 'assimp.gltf', 'core.particle', 'core.wireframe', 'mesh.wire', 'pars.base',
           'pars.simple', 'pars.trans', 'scene.raster']
 
 

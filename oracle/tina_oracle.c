@@ -779,6 +779,74 @@ void orc_bloom(float *image, int W, int H, const float *gwei, int radius, float 
 /* ---- mesh providers feeding set_object ------------------------------------------ */
 
 /* mesh/grid.py:26-35 MeshGrid.pre_compute; pos, nrm: [nx][ny][3] */
+/* postp/ssao.py:65-96 render_at for every pixel (non-TAA mode: fixed sample / rotation tables, :24-36).
+ * depth: int32 [W][H] (engine.depth), normals: [W][H][3] (the scene's NormalShader buffer), out ao: [W][H] */
+void orc_ssao_render(const int32_t *depth, const float *normals, const float *W2V, const float *V2W, const float *bias,
+                     int W, int H, const float *samples, int nsamples, const float *rotations, int noise, float radius,
+                     float thresh, float factor, float *ao) {
+    const float up[3] = {233.0f, 666.0f, 512.0f}; /* advans.py:97 */
+    for (int i = 0; i < W; i++)
+        for (int j = 0; j < H; j++) {
+            const int64_t P = (int64_t)i * H + j;
+            const float *normal = normals + P * 3;
+            const float p[2] = {(float)i + bias[0], (float)j + bias[1]};
+            float vpos[3] = {p[0] / (float)W * 2.0f - 1.0f, p[1] / (float)H * 2.0f - 1.0f, (float)depth[P] / 1073741824.0f};
+            float pos[3];
+            mapply_pos(V2W, vpos, pos);
+            /* shader.py:82-93 calc_viewdir */
+            float q[3] = {vpos[0], vpos[1], -1.0f}, ro[3], ro1[3], rd[3];
+            mapply_pos(V2W, q, ro);
+            q[2] = 1.0f;
+            mapply_pos(V2W, q, ro1);
+            for (int k = 0; k < 3; k++) rd[k] = ro1[k] - ro[k];
+            normalize3(rd);
+            const float viewdir[3] = {-rd[0], -rd[1], -rd[2]};
+            float t3[3], tv[3];
+            for (int k = 0; k < 3; k++) t3[k] = pos[k] - radius * viewdir[k];
+            mapply_pos(W2V, t3, tv);
+            const float vradius = tv[2] - vpos[2];
+            /* advans.py:97-100 tangentspace(normal) */
+            float bitan[3], tan[3];
+            cross3(normal, up, bitan);
+            normalize3(bitan);
+            cross3(bitan, normal, tan);
+            const float *rot = rotations + ((int64_t)(i % noise) * noise + (j % noise)) * 2;
+            float occ = 0.0f;
+            for (int s = 0; s < nsamples; s++) {
+                const float *sm = samples + (int64_t)s * 3;
+                const float sx = rot[0] * sm[0] + rot[1] * sm[1], sy = -rot[0] * sm[0] + rot[1] * sm[1], sz = sm[2]; /* :86-88 */
+                float sp[3], sv[3];
+                for (int k = 0; k < 3; k++) sp[k] = pos[k] + ((tan[k] * sx + bitan[k] * sy) + normal[k] * sz) * radius;
+                mapply_pos(W2V, sp, sv);
+                const float Dx = (sv[0] * 0.5f + 0.5f) * (float)W, Dy = (sv[1] * 0.5f + 0.5f) * (float)H;
+                if (0.0f <= Dx && Dx < (float)W && 0.0f <= Dy && Dy < (float)H) {
+                    const float d = (float)depth[(int64_t)f2i(Dx) * H + f2i(Dy)] / 1073741824.0f;
+                    if (d < sv[2]) {
+                        float rc = vradius / (vpos[2] - d);
+                        const float t = clamp01((fabsf(rc) - 0.0f) / (1.0f - 0.0f)); /* common.py:216-218 smoothstep */
+                        occ += t * t * (3.0f - 2.0f * t);
+                    }
+                }
+            }
+            float a = occ / (float)nsamples;
+            a = factor * (a - thresh);
+            ao[P] = clamp01(a);
+        }
+}
+
+/* postp/ssao.py:38-49 apply (non-TAA): out *= 1 - box(noise x noise)(ao) / noise^2; reads outside the field are 0 */
+void orc_ssao_apply(float *image, const float *ao, int W, int H, int noise) {
+    const int offs = noise / 2;
+    for (int i = 0; i < W; i++)
+        for (int j = 0; j < H; j++) {
+            float r = 0.0f;
+            for (int k = 0; k < noise; k++)
+                for (int l = 0; l < noise; l++) r += ld2(ao, W, H, i + k - offs, j + l - offs);
+            const float f = 1.0f - r / (float)(noise * noise);
+            for (int c = 0; c < 3; c++) image[((int64_t)i * H + j) * 3 + c] *= f;
+        }
+}
+
 void orc_grid_normals(const float *pos, int nx, int ny, float *nrm) {
     for (int i = 0; i < nx; i++)
         for (int j = 0; j < ny; j++) {

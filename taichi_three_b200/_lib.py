@@ -96,6 +96,8 @@ SIGNATURES = {
     'tina_wire_render_color': (_i, [_vp, C.POINTER(_vp), _i, _vp]),
     'tina_image_fill': (_i, [_vp, _i64, _fp, _vp]),
     'tina_image_tonemap': (_i, [_vp, _i64, _vp]),
+    'tina_engine_ssao_render': (_i, [_vp, _vp, _vp, _i, _vp, _i, _f, _f, _f, _vp, _vp]),
+    'tina_image_ssao_apply': (_i, [_vp, _vp, _i, _i, _i, _vp]),
     'tina_image_fxaa': (_i, [_vp, _i, _i, _vp, _vp, _f, _f, _f, _vp]),
     'tina_image_bloom': (_i, [_vp, _i, _i, _vp, _vp, _vp, _i, _f, _f, _f, _vp]),
     'tina_image_accumulate': (_i, [_vp, _vp, _i64, _i, _vp]),

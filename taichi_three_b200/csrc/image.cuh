@@ -120,6 +120,60 @@ static int material_kind(const TinaMaterial *m) {
     return MAT_GENERIC;
 }
 
+// ---- SSAO (postp/ssao.py, non-TAA mode: sample and rotation tables fixed at construction) ----
+// postp/ssao.py:65-96 render_at; same op order as the reference (the AO term has hard tests: d < sample.z, D inside)
+__global__ void __launch_bounds__(256)
+k_ssao_render(const long long *__restrict__ keys, const float *__restrict__ normals, const __grid_constant__ Cam cam,
+              const float *__restrict__ samples, int nsamples, const float *__restrict__ rotations, int noise, float radius,
+              float thresh, float factor, float *__restrict__ ao) {
+    const int P = blockIdx.x * blockDim.x + threadIdx.x;
+    if (P >= cam.W * cam.H) return;
+    const int i = P / cam.H, j = P - i * cam.H;
+    const V3 normal = v3(normals[(long long)P * 3], normals[(long long)P * 3 + 1], normals[(long long)P * 3 + 2]);
+    const float px = (float)i + cam.bias[0], py = (float)j + cam.bias[1];
+    const float vx = px / cam.fW * 2.0f - 1.0f, vy = py / cam.fH * 2.0f - 1.0f;
+    const float vz = (float)(int)(keys[P] >> 32) / 1073741824.0f;
+    const V3 pos = mapply_pos3(cam.V2W, vx, vy, vz);
+    const V3 viewdir = view_direction<false>(cam, px, py);
+    const float vradius = mapply_pos3(cam.W2V, pos.x - radius * viewdir.x, pos.y - radius * viewdir.y, pos.z - radius * viewdir.z).z - vz;
+    const V3 bitan = normalized(cross3(normal, v3(233.0f, 666.0f, 512.0f))); // advans.py:97-100 tangentspace
+    const V3 tan = cross3(bitan, normal);
+    const float *rot = rotations + ((long long)(i % noise) * noise + (j % noise)) * 2;
+    const float r0 = rot[0], r1 = rot[1];
+    float occ = 0.0f;
+    for (int s = 0; s < nsamples; s++) {
+        const float s0 = __ldg(samples + s * 3), s1 = __ldg(samples + s * 3 + 1), sz = __ldg(samples + s * 3 + 2);
+        const float sx = r0 * s0 + r1 * s1, sy = -r0 * s0 + r1 * s1; // ssao.py:86-88 (sic: not a rotation matrix)
+        const V3 sv = mapply_pos3(cam.W2V, pos.x + ((tan.x * sx + bitan.x * sy) + normal.x * sz) * radius,
+                                  pos.y + ((tan.y * sx + bitan.y * sy) + normal.y * sz) * radius,
+                                  pos.z + ((tan.z * sx + bitan.z * sy) + normal.z * sz) * radius);
+        const float Dx = (sv.x * 0.5f + 0.5f) * cam.fW, Dy = (sv.y * 0.5f + 0.5f) * cam.fH;
+        if (0.0f <= Dx && Dx < cam.fW && 0.0f <= Dy && Dy < cam.fH) {
+            const float d = (float)(int)(keys[(long long)f2i(Dx) * cam.H + f2i(Dy)] >> 32) / 1073741824.0f;
+            if (d < sv.z) {
+                const float rc = vradius / (vz - d);
+                const float t = clamp01((fabsf(rc) - 0.0f) / (1.0f - 0.0f));
+                occ += t * t * (3.0f - 2.0f * t);
+            }
+        }
+    }
+    float a = occ / (float)nsamples;
+    a = factor * (a - thresh);
+    ao[P] = clamp01(a);
+}
+
+// postp/ssao.py:38-49 apply: out *= 1 - box(noise x noise)(ao) / noise^2 (reads outside the field are 0)
+__global__ void k_ssao_apply(float *__restrict__ image, const float *__restrict__ ao, int W, int H, int noise) {
+    const int P = blockIdx.x * blockDim.x + threadIdx.x;
+    if (P >= W * H) return;
+    const int i = P / H, j = P - i * H, offs = noise / 2;
+    float r = 0.0f;
+    for (int k = 0; k < noise; k++)
+        for (int l = 0; l < noise; l++) r += ld2(ao, W, H, i + k - offs, j + l - offs);
+    const float f = 1.0f - r / (float)(noise * noise);
+    image[(long long)P * 3] *= f, image[(long long)P * 3 + 1] *= f, image[(long long)P * 3 + 2] *= f;
+}
+
 // ------------------------------------------------------------------------------------
 // self-test: div_many against __fdiv_rn
 // ------------------------------------------------------------------------------------

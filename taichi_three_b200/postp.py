@@ -1,5 +1,6 @@
-"""Image-space post effects on the raster path's image: FXAA and Blooming (reference tina/postp/fxaa.py,
-tina/postp/blooming.py) over tina_image_fxaa / tina_image_bloom of libtina_b200."""
+"""Image-space post effects on the raster path's image: FXAA, Blooming and SSAO (reference tina/postp/fxaa.py,
+tina/postp/blooming.py, tina/postp/ssao.py) over tina_image_fxaa / tina_image_bloom / tina_engine_ssao_render of
+libtina_b200."""
 import ctypes as C
 
 import numpy as np
@@ -72,3 +73,55 @@ class Blooming:
                                                C.c_void_p(self._b.data_ptr()), C.c_void_p(self._gwei.data_ptr()), key[0],
                                                float(self.thresh[None]), float(self.scale[None]), float(self.factor[None]),
                                                _stream()))
+
+
+class SSAO:
+    """Screen-space ambient occlusion (postp/ssao.py), non-TAA mode: a fixed table of hemisphere samples and a small
+    tile of per-pixel rotations, drawn once at construction like the reference (:24-36, :51-56); `norm` is the scene's
+    world-normal G-buffer.  The tables are plain tensors (`samples`, `rotations`) and may be overwritten."""
+
+    def __init__(self, res, norm, nsamples=64, thresh=0.0, radius=0.2, factor=1.0, noise_size=4, taa=False, seed=None):
+        if taa:
+            raise NotImplementedError('SSAO(taa=True) draws fresh random samples per pixel and frame; only the table mode is implemented')
+        self.res = (int(res[0]), int(res[1]))
+        self.norm = norm
+        self.radius = HostField(np.float32(radius))
+        self.thresh = HostField(np.float32(thresh))
+        self.factor = HostField(np.float32(factor))
+        self.nsamples = int(nsamples)
+        self.noise_size = int(noise_size)
+        dev = (norm.to_torch() if hasattr(norm, 'to_torch') else norm).device
+        from .field import Field
+        self.img = Field(torch.zeros(self.res, dtype=torch.float32, device=dev))
+        self.seed_samples(seed)
+
+    def seed_samples(self, seed=None):
+        """ssao.py:30-36, 51-56 in float32: make_sample() = spherical(lerp(u, .01, 1), v) * lerp(w**1.5, .01, 1)."""
+        rng = np.random.default_rng(seed)
+        f = np.float32
+        u, v, w = (rng.random(self.nsamples).astype(f) for _ in range(3))
+        r = f(0.01) * (f(1) - w ** f(1.5)) + f(1.0) * w ** f(1.5)
+        h = f(0.01) * (f(1) - u) + f(1.0) * u
+        s = np.sqrt(np.maximum(f(0), f(1) - h * h))
+        tau = f(2 * np.pi)
+        smp = np.stack([s * np.cos(v * tau), s * np.sin(v * tau), h], axis=1) * r[:, None]
+        t = tau * rng.random((self.noise_size, self.noise_size)).astype(f)
+        dev = self.img.to_torch().device
+        self.samples = torch.as_tensor(np.ascontiguousarray(smp, dtype=f), device=dev)
+        self.rotations = torch.as_tensor(np.ascontiguousarray(np.stack([np.cos(t), np.sin(t)], axis=2), dtype=f), device=dev)
+
+    def render(self, engine):  # ssao.py:58-96
+        n = self.norm.to_torch() if hasattr(self.norm, 'to_torch') else self.norm
+        if n.dtype != torch.float32 or not n.is_contiguous() or tuple(n.shape) != (self.res[0], self.res[1], 3):
+            raise ValueError('SSAO needs a contiguous float32 [W, H, 3] normal buffer')
+        smp, rot = self.samples.contiguous(), self.rotations.contiguous()
+        _lib.check(_lib.lib().tina_engine_ssao_render(engine._h, C.c_void_p(n.data_ptr()), C.c_void_p(smp.data_ptr()), int(smp.shape[0]),
+                                                      C.c_void_p(rot.data_ptr()), int(rot.shape[0]), float(self.radius[None]),
+                                                      float(self.thresh[None]), float(self.factor[None]),
+                                                      C.c_void_p(self.img.to_torch().data_ptr()), _stream()))
+        self._keep = (n, smp, rot)
+
+    def apply(self, out):  # ssao.py:38-49
+        t = _img(out)
+        _lib.check(_lib.lib().tina_image_ssao_apply(C.c_void_p(t.data_ptr()), C.c_void_p(self.img.to_torch().data_ptr()), t.shape[0],
+                                                    t.shape[1], self.noise_size, _stream()))

@@ -1,7 +1,7 @@
 """Scene: frame orchestration for the raster pipeline (reference tina/scene/raster.py:5-258),
 restricted to the triangle-raster path: objects -> set_object / render_occup / render_color,
-default light + ambient, ACES tonemap.  Options that enable other subsystems (ibl, ssr, ssao,
-fxaa, blooming, taa) are outside this path and raise."""
+default light + ambient, ACES tonemap, and the image-space passes ssao / blooming / fxaa / taa in the reference's
+order.  Options that enable other subsystems (ibl, ssr) raise."""
 import numpy as np
 import torch
 
@@ -40,7 +40,7 @@ class Accumator:
 
 
 class Scene:
-    UNSUPPORTED = ('ibl', 'ssr', 'ssao')
+    UNSUPPORTED = ('ibl', 'ssr')
 
     def __init__(self, res_x=512, res_y=None, **options):
         self.engine = Engine(res_x, res_y)
@@ -69,6 +69,14 @@ class Scene:
         if self.fxaa:  # raster.py:82-83
             from .postp import FXAA
             self.fxaa = FXAA(self.res)
+        self.ssao = options.get('ssao', False)
+        if self.ssao:  # raster.py:51-54, 65-66: world-normal G-buffer as a pre-shader + the SSAO pass
+            from .postp import SSAO
+            from .shader import NormalShader
+            self.norm_buffer = Field(torch.zeros((self.res[0], self.res[1], 3), dtype=torch.float32, device=self.engine.device))
+            self.norm_shader = NormalShader(self.norm_buffer)
+            self.pre_shaders.append(self.norm_shader)
+            self.ssao = SSAO(self.res, self.norm_buffer, taa=self.taa)
         if self.taa:
             self.accum = Accumator(self.res, self.engine.device)
         # raster.py:90-93
@@ -132,7 +140,7 @@ class Scene:
         bg = np.broadcast_to(np.asarray(self.bgcolor, dtype=np.float32), (3,))
         if not items:
             self.image.fill(bg)
-        fuse_tm = bool(self.tonemap) and len(items) == 1 and not self.blooming
+        fuse_tm = bool(self.tonemap) and len(items) == 1 and not self.blooming and not self.ssao
         for i, (obj, info) in enumerate(items):
             shader = self.shaders[id(info.material)]
             info.raster.set_object(obj)
@@ -143,6 +151,9 @@ class Scene:
                 if i == 0:
                     self.image.fill(bg)
                 info.raster.render_color(shader)
+        if self.ssao:  # raster.py:189-191
+            self.ssao.render(self.engine)
+            self.ssao.apply(self.image)
         if self.blooming:  # raster.py:200-201
             self.blooming.apply(self.image)
         if self.tonemap and not fuse_tm:

@@ -325,6 +325,35 @@ def case_postfx():
     print('postfx: fxaa changed', int((np.abs(out['fxaa'] - img).max(-1) > 0).sum()), 'bloom mean', float((out['bloom'] - img).mean()))
 
 
+def case_ssao():
+    """postp/ssao.py inside Scene(ssao=True) (scene/raster.py:51-66,189-191): the normal G-buffer, the (random, but
+    fixed at construction) sample and rotation tables, the AO field and the image before / after SSAO.apply."""
+    np.random.seed(11)
+    scene = tina.Scene((48, 40), smoothing=True, ssao=True, tonemap=False)
+    scene.add_object(tina.MeshModel(os.path.join(REF, 'assets/monkey.obj')))
+    camera(scene, 48 / 40)
+    eng = scene.engine
+    scene.image.fill(scene.bgcolor)
+    eng.clear_depth()
+    for sh in scene.pre_shaders + scene.post_shaders:
+        sh.clear_buffer()
+    for obj, oinfo in scene.objects.items():
+        oinfo.raster.set_object(obj)
+        oinfo.raster.render_occup()
+        oinfo.raster.render_color(scene.shaders[oinfo.material])
+    out = {'W2V': eng.W2V.to_numpy().astype(np.float32), 'V2W': eng.V2W.to_numpy().astype(np.float32),
+           'depth': eng.depth.to_numpy().astype(np.int32), 'normals': scene.norm_buffer.to_numpy().astype(np.float32),
+           'samples': scene.ssao.samples.to_numpy().astype(np.float32), 'rotations': scene.ssao.rotations.to_numpy().astype(np.float32),
+           'image_before': scene.image.to_numpy().astype(np.float32)}
+    scene.ssao.render(eng)
+    out['ao'] = scene.ssao.img.to_numpy().astype(np.float32)
+    scene.ssao.apply(scene.image)
+    out['image_after'] = scene.image.to_numpy().astype(np.float32)
+    path = os.path.join(HERE, 'particles_ssao.npz')  # (particles_ prefix = not a plain raster scene, see test_golden.CASES)
+    np.savez_compressed(path, **out)
+    print('particles_ssao: ao mean %.4f max %.4f, %d B' % (out['ao'].mean(), out['ao'].max(), os.path.getsize(path)))
+
+
 def case_micro():
     """The C2 regime at golden size: sub-pixel faces.  (a) MeshGrid(56) wave on a 40x30 screen (~0.3 px per face,
     smooth normals, Classic) -- most faces cover no sample, many samples lie within 1e-2 px of an edge;
@@ -361,6 +390,7 @@ if __name__ == '__main__':
             globals()['case_' + name]()
         sys.exit(0)
     case_micro()
+    case_ssao()
     case_monkey()
     case_grid()
     case_cornell()

@@ -229,3 +229,13 @@ def test_oracle_postfx_match_reference_sources(tina, O):
     assert np.abs(gw - g['gwei']).max() <= 2e-8
     assert np.array_equal(O.bloom(g['input'], g['gwei']), g['bloom'])
     assert np.abs(O.bloom(g['input'], gw) - g['bloom']).max() <= 1e-6
+
+
+def test_oracle_ssao_matches_reference_sources(tina, O):
+    """postp/ssao.py run from the reference's own sources under the shim (golden: depth, normal G-buffer, the sample /
+    rotation tables it drew, the AO field, the image before and after apply) against the oracle restatement."""
+    g = np.load(os.path.join(GOLDEN, 'particles_ssao.npz'))
+    ao = O.ssao_render(g['depth'], g['normals'], g['W2V'], g['V2W'], g['samples'], g['rotations'])
+    assert g['ao'].max() > 0.3 and (g['ao'] > 0).sum() > 100
+    assert np.array_equal(ao, g['ao'])
+    assert np.array_equal(O.ssao_apply(g['image_before'], g['ao']), g['image_after'])

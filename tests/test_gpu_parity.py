@@ -916,3 +916,53 @@ def test_shared_divisor_division_is_ieee(tina):
         bad = C.c_uint64(123)
         _lib.check(_lib.lib().tina_selftest_division(0, 3 * 10**9, seed, C.byref(bad)))
         assert bad.value == 0
+
+
+def test_ssao_matches_reference_golden_and_scene_option(tina, O):
+    """§8f row 4: SSAO kernels on the golden's inputs (depth, normals, tables from the reference's own run) and
+    Scene(ssao=True) end to end against the oracle applied to this pipeline's own depth / normal buffers."""
+    import os
+    import torch
+    from test_golden import GOLDEN
+    g = np.load(os.path.join(GOLDEN, 'particles_ssao.npz'))
+    W, H = g['depth'].shape
+    eng = tina.Engine((W, H))
+    eng.W2V[None], eng.V2W[None] = g['W2V'], g['V2W']
+    eng.keys.copy_(torch.as_tensor(g['depth'].astype(np.int64) << 32).cuda())
+    norm = tina.Field(torch.as_tensor(g['normals']).cuda())
+    ssao = tina.SSAO((W, H), norm)
+    ssao.samples, ssao.rotations = torch.as_tensor(g['samples']).cuda(), torch.as_tensor(g['rotations']).cuda()
+    ssao.render(eng)
+    torch.cuda.synchronize()
+    ao = ssao.img.to_numpy()
+    assert np.abs(ao - g['ao']).max() <= 1e-6 and (ao != g['ao']).mean() < 0.01
+    img = tina.Field(torch.as_tensor(g['image_before']).cuda())
+    ssao.img.from_numpy(g['ao'])
+    ssao.apply(img)
+    assert np.abs(img.to_numpy() - g['image_after']).max() <= 1e-6
+    # the Scene option: normal G-buffer pre-shader + render + apply before the tonemap (raster.py:51-66, 189-191)
+    obj = scenes.load_monkey()
+    scene = tina.Scene((96, 80), smoothing=True, ssao=True)
+    scene.add_object(tina.MeshModel(obj))
+    view, proj = scenes.default_camera(96 / 80)
+    scene.engine.set_camera(view, proj)
+    scene.render()
+    torch.cuda.synchronize()
+    depth, nrm = scene.engine.depth.to_numpy(), scene.norm_buffer.to_numpy()
+    W2V = (np.asarray(proj, np.float64) @ np.asarray(view, np.float64))
+    ao_ref = O.ssao_render(depth, nrm, W2V.astype(np.float32), np.linalg.inv(W2V).astype(np.float32), scene.ssao.samples.cpu().numpy(),
+                           scene.ssao.rotations.cpu().numpy())
+    ao_gpu = scene.ssao.img.to_numpy()
+    assert ao_ref.max() > 0.2
+    assert np.abs(ao_gpu - ao_ref).max() <= 1e-6 and (ao_gpu != ao_ref).mean() < 0.01
+    scene2 = tina.Scene((96, 80), smoothing=True)
+    scene2.add_object(tina.MeshModel(obj))
+    scene2.engine.set_camera(view, proj)
+    scene2.triangle_raster.set_tuning(fast_shading=0)
+    scene.triangle_raster.set_tuning(fast_shading=0)
+    scene.render()
+    scene2.tonemap = False
+    scene2.render()
+    torch.cuda.synchronize()
+    expect = O.tonemap(O.ssao_apply(scene2.img.to_numpy(), scene.ssao.img.to_numpy()))
+    assert np.abs(scene.img.to_numpy() - expect).max() <= 1e-6
