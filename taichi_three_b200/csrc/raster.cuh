@@ -412,7 +412,9 @@ __device__ __forceinline__ void walk_candidates(const FaceA &f, const Setup &s, 
 // mode 0 (no NoCulling / flip wrappers), 3 = expanded arrays -- which removes the option tests from the per-face
 // path (C2: K1 43.6 -> 39.0 us).
 template <bool IDX, int LEAN = 0>
-__global__ void __launch_bounds__(K1_THREADS, 6)
+// (register budget: 40 for the indexed variants -- C2 is fastest there -- and 41-42 for the expanded-array ones, whose
+// shared walk then keeps its shared-memory addresses in registers: C3 1.67 -> 1.57 ms; six CTAs per SM either way)
+__global__ void __launch_bounds__(K1_THREADS, IDX ? 6 : 5)
 k_raster_faces(const float *__restrict__ verts, long long nfaces, const __grid_constant__ Cam cam, uint32_t flags_rt,
                unsigned base, long long *__restrict__ keys, uint4 *__restrict__ queue, unsigned *__restrict__ counters,
                unsigned queue_cap, int tiny_max, int tighten_rt, int precheck_rt, int balance, int collect_stats_rt,
