@@ -191,6 +191,14 @@ def main():
             k = engine.keys
             out['keys_checksum'] = int((k ^ (k >> 29)).sum().item())
             out['covered'] = int(((k & 0xffffffff) != 0).sum().item())
+            if world == 1 and N <= 2**24:
+                # C5 against the CPU oracle on a 2^24-face prefix of the same soup (same generator, same seed)
+                from oracle import oracle as O
+                t0 = time.time()
+                occup, depth, tie, st = O.render_occup(tri.cpu().numpy(), (proj @ view).astype(np.float32), W, H)
+                d, o = M.unpack_keys(engine.keys.cpu().view(W, H))
+                out['oracle'] = dict(depth_equal=bool(np.array_equal(d.numpy(), depth)), occup_equal=bool(np.array_equal(o.numpy(), occup)),
+                                     covered_per_face=st['covered'] / N, tie_pixels=int(tie.sum()), oracle_s=time.time() - t0)
             if world > 1:
                 dist.barrier()
             out['image_sum'] = float(img.to_torch().double().sum().item())  # (root gather: every rank reads the root's memory)
