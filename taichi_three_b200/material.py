@@ -355,6 +355,10 @@ def fold_program(code, color_is_one=True):
             w, f = stack.pop(), stack.pop()
             if w[0] == f[0] == 'c':
                 stack.append(('c', f[1] * w[1]))
+            elif w[0] == 'c' and np.all(w[1] == _F(1)):
+                stack.append(f)  # x * 1 == x bit for bit (PBR's `basecolor * color` with color = 1)
+            elif f[0] == 'c' and np.all(f[1] == _F(1)):
+                stack.append(w)
             else:
                 push_dyn([f, w], ins)
         elif op == _lib.OP_ADD:
@@ -411,6 +415,18 @@ def hoist_programs(brdf, amb, emi):
     parameters keep the [X, X, ..., COOK|PHONG, MIX] shapes the specialised shading kernels recognise."""
     regs = {}      # structural key -> register index
     prologue = []  # postfix code
+    # sub-expressions that occur more than once (tina.PBR: the Fresnel factor of the sampled base colour feeds the
+    # specular colour, the diffuse weight and the ambient term) are evaluated once, into a register of their own
+    trees = [_to_tree(code) for code in (brdf, amb, emi)]
+    seen_count = {}
+
+    def count(tree):
+        if tree[0] not in (_lib.OP_CONST, _lib.OP_REG, _lib.OP_INPUT):
+            seen_count[tree] = seen_count.get(tree, 0) + 1
+        for k in tree[3:]:
+            count(k)
+    for t in trees:
+        count(t)
 
     def reg_of(tree):
         """emit `tree` (light independent, not constant) into the prologue; -> OP_REG leaf"""
@@ -428,8 +444,8 @@ def hoist_programs(brdf, amb, emi):
         return (_lib.OP_REG, r, (0.0, 0.0, 0.0))
 
     def hoist_li(tree):
-        """inside a light-independent expression: only texture samples are worth a register"""
-        if tree[0] == _lib.OP_TEXTURE:
+        """inside a light-independent expression: texture samples and repeated sub-expressions get a register"""
+        if tree[0] == _lib.OP_TEXTURE or seen_count.get(tree, 0) >= 2:
             return reg_of(tree)
         return tree[:3] + tuple(hoist_li(k) for k in tree[3:])
 
@@ -440,7 +456,7 @@ def hoist_programs(brdf, amb, emi):
             return reg_of(tree)
         return tree[:3] + tuple(hoist(k) for k in tree[3:])
 
-    out = [_to_code(hoist(_to_tree(code)), []) for code in (brdf, amb, emi)]
+    out = [_to_code(hoist(t), []) for t in trees]
     return out[0], out[1], out[2], prologue
 
 
