@@ -112,15 +112,21 @@ __device__ __forceinline__ V3 op_cook(V3 ro, V3 f0, V3 nrm, V3 idir, V3 odir) { 
     float VoH = fminf(1.0f, fmaxf(EPS, dot3(half, odir))); // 1 - 1e-10 == 1.0f
     float fr = powf(1.0f - VoH, 5.0f);
     float rr[3] = {ro.x, ro.y, ro.z}, ff[3] = {f0.x, f0.y, f0.z}, o[3];
+    // a grey roughness (the usual case) gives the same D and G for the three channels: evaluate them once --
+    // the same operations on the same values, hence the same bits as the per-channel loop of the reference
+    const bool grey = ro.x == ro.y && ro.x == ro.z;
+    float ndf = 0.0f, vdf = 0.0f;
 #pragma unroll
     for (int k = 0; k < 3; k++) {
-        float alpha2 = fmaxf(eps, rr[k] * rr[k]);
-        float denom = 1.0f - (NoH * NoH) * (1.0f - alpha2);
-        float ndf = alpha2 / (denom * denom);
-        float kk = alpha2 / 2.0f;
-        float vdf = 1.0f / ((NoV * kk + 1.0f) - kk);
-        vdf *= 1.0f / ((NoL * kk + 1.0f) - kk);
-        vdf /= 1.0f * (1.0f - alpha2) + 12.566370614359172f * alpha2; // common.py:221-223 lerp(alpha2, 1, 4 pi)
+        if (k == 0 || !grey) {
+            float alpha2 = fmaxf(eps, rr[k] * rr[k]);
+            float denom = 1.0f - (NoH * NoH) * (1.0f - alpha2);
+            ndf = alpha2 / (denom * denom);
+            float kk = alpha2 / 2.0f;
+            vdf = 1.0f / ((NoV * kk + 1.0f) - kk);
+            vdf *= 1.0f / ((NoL * kk + 1.0f) - kk);
+            vdf /= 1.0f * (1.0f - alpha2) + 12.566370614359172f * alpha2; // common.py:221-223 lerp(alpha2, 1, 4 pi)
+        }
         float fdf = ff[k] + (1.0f - ff[k]) * fr;
         o[k] = fdf * vdf * ndf;
     }
