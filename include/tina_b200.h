@@ -102,7 +102,10 @@ typedef struct {
     /* optional 4th program after emission: run ONCE per pixel before lighting; it evaluates the
      * light-independent, non-constant sub-expressions the host hoisted out of the other three
      * (texture samples, Fresnel factors, ...) into registers they then read with TINA_OP_REG */
-    int32_t n_prologue, pad_[3];
+    int32_t n_prologue;     /* TinaInstr slots of the prologue program (after brdf, ambient, emission in code[]) */
+    int32_t prologue_form;  /* 0: interpret it; 1: it is the 24-slot prologue of tina.PBR with a textured base colour
+                             * (TEXTURE -> r0, Fresnel -> r1, diffuse -> r2, ambient -> r3, emission -> r4): run as straight-line code */
+    int32_t pad_[2];
     TinaInstr code[TINA_MAX_INSTR];
 } TinaMaterial;
 

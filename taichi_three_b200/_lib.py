@@ -36,7 +36,7 @@ class TinaMaterial(C.Structure):
                 ('tex', C.c_void_p * TINA_MAX_TEX),
                 ('tex_w', C.c_int32 * TINA_MAX_TEX), ('tex_h', C.c_int32 * TINA_MAX_TEX),
                 ('tex_c', C.c_int32 * TINA_MAX_TEX),
-                ('n_prologue', C.c_int32), ('pad_', C.c_int32 * 3),
+                ('n_prologue', C.c_int32), ('prologue_form', C.c_int32), ('pad_', C.c_int32 * 2),
                 ('code', TinaInstr * TINA_MAX_INSTR)]
 
 

@@ -212,6 +212,25 @@ __device__ V3 run_program(const TinaMaterial &m, int begin, int n, const ShadeIn
     return sp > 0 ? st[sp - 1] : v3(0.f, 0.f, 0.f);
 }
 
+// TinaMaterial.prologue_form == 1: the prologue of tina.PBR with a textured base colour (matr/material.py:701-706 after
+// the host's folding / hoisting), slot layout in material.py:_PBR_TEX_PROLOGUE.  The same operations in the same order
+// as interpreting those 24 slots -- without 24 interpreter dispatches and their local-memory stack traffic.
+__device__ __forceinline__ void prologue_pbr_textured(const TinaMaterial &m, int b, const ShadeIn &in, V3 *regs) {
+    auto C = [&](int i) { return v3(m.code[b + i].c[0], m.code[b + i].c[1], m.code[b + i].c[2]); };
+    const int t = m.code[b + 1].arg;
+    const V3 base = tex_sample(m.tex[t], m.tex_w[t], m.tex_h[t], m.tex_c[t], in.texcoord.x, in.texcoord.y);
+    const V3 me = C(3), sp = C(5);
+    V3 fr; // material.py:69-83
+    fr.x = me.x * base.x + (1.0f - me.x) * 0.16f * (sp.x * sp.x);
+    fr.y = me.y * base.y + (1.0f - me.y) * 0.16f * (sp.y * sp.y);
+    fr.z = me.z * base.z + (1.0f - me.z) * 0.16f * (sp.z * sp.z);
+    const V3 k9 = C(9), k19 = C(19);
+    regs[0] = base, regs[1] = fr;
+    regs[2] = v3(base.x * k9.x, base.y * k9.y, base.z * k9.z);
+    regs[3] = op_mix(fr, base, C(14));
+    regs[4] = op_mix(fr, v3(base.x * k19.x, base.y * k19.y, base.z * k19.z), C(21));
+}
+
 // operand i of a specialised brdf shape: a constant or a prologue register
 __device__ __forceinline__ V3 operand(const TinaMaterial &m, int i, const V3 *regs) {
     if (m.code[i].op == TINA_OP_REG) return regs[m.code[i].arg & (TINA_MAX_REGS - 1)];
@@ -392,7 +411,8 @@ __device__ __forceinline__ V3 light_pixel(const ShadeIn &in, V3 viewdir, const T
     } else {
         if (mat.n_prologue) { // light-independent sub-expressions (texture samples, Fresnel factors ...), once per pixel
             const V3 zero = v3(0.f, 0.f, 0.f);
-            run_program(mat, mat.n_brdf + mat.n_ambient + mat.n_emission, mat.n_prologue, in, zero, zero, zero, regs);
+            if (mat.prologue_form == 1) prologue_pbr_textured(mat, mat.n_brdf + mat.n_ambient + mat.n_emission, in, regs);
+            else run_program(mat, mat.n_brdf + mat.n_ambient + mat.n_emission, mat.n_prologue, in, zero, zero, zero, regs);
         }
         V3 em = run_or_const(mat, mat.n_brdf + mat.n_ambient, mat.n_emission, in, regs);
         res.x += em.x, res.y += em.y, res.z += em.z;

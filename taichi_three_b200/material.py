@@ -482,6 +482,26 @@ def param_signature(material):
     return tuple(p._value.tobytes() for p in params)
 
 
+# prologue of tina.PBR(basecolor=Texture(...)) with constant metallic / roughness / specular after folding, CSE and
+# hoisting: (op, arg) per slot, None = any constant.  The device runs this shape as straight-line code.
+_PBR_TEX_PROLOGUE = [(_lib.OP_INPUT, 3), (_lib.OP_TEXTURE, None), (_lib.OP_STORE, 0),
+                     (_lib.OP_CONST, None), (_lib.OP_REG, 0), (_lib.OP_CONST, None), (_lib.OP_FRESNEL, None), (_lib.OP_STORE, 1),
+                     (_lib.OP_REG, 0), (_lib.OP_CONST, None), (_lib.OP_MUL, None), (_lib.OP_STORE, 2),
+                     (_lib.OP_REG, 1), (_lib.OP_REG, 0), (_lib.OP_CONST, None), (_lib.OP_MIX, None), (_lib.OP_STORE, 3),
+                     (_lib.OP_REG, 1), (_lib.OP_REG, 0), (_lib.OP_CONST, None), (_lib.OP_MUL, None), (_lib.OP_CONST, None),
+                     (_lib.OP_MIX, None), (_lib.OP_STORE, 4)]
+
+
+def prologue_form(pro):
+    """1 if `pro` is the textured-PBR prologue shape (include/tina_b200.h, TinaMaterial.prologue_form), else 0."""
+    if len(pro) != len(_PBR_TEX_PROLOGUE):
+        return 0
+    for (op, arg, _), (top, targ) in zip(pro, _PBR_TEX_PROLOGUE):
+        if op != top or (targ is not None and arg != targ):
+            return 0
+    return 1
+
+
 def compile_material(material, fold=True, color_is_one=True):
     """flatten -> constant-fold -> hoist.  -> (brdf, ambient, emission, prologue, textures)"""
     brdf, amb, emi, textures = flatten_material(material)
@@ -500,6 +520,7 @@ def material_struct(material, device, fold=True, color_is_one=True):
     m = _lib.TinaMaterial()
     m.n_brdf, m.n_ambient, m.n_emission, m.ntex = len(brdf), len(amb), len(emi), len(textures)
     m.n_prologue = len(pro)
+    m.prologue_form = prologue_form(pro)
     keep = []
     for i, t in enumerate(textures):
         d = t.device_tensor(device)
