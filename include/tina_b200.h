@@ -86,6 +86,14 @@ enum {
     TINA_OP_STORE = 11,  /* pop -> register[arg]                                                         */
 };
 #define TINA_MAX_REGS 8
+/* Three-address prologue (TinaMaterial.prologue_form = 2), produced by the host compiler from the postfix prologue: one
+ * header slot per operation, op = TINA_OP3 | <postfix op>, arg = dst | s0 << 8 | s1 << 16 | s2 << 24 with source codes
+ * 0..15 = value register (0..7 are the registers the other programs read with TINA_OP_REG, 8..15 temporaries),
+ * 16..19 = TINA_OP_INPUT 0..3, 255 = the constant in the next slot's c[] (slots are consumed in source order).
+ * TINA_OP_TEXTURE keeps its texture slot in c[0] of the header; (TINA_OP3 | TINA_OP_REG) copies s0 to dst.
+ * Same operations on the same values as the postfix form, a third to a quarter of the interpreter steps. */
+#define TINA_OP3 0x100
+#define TINA_VM_VALUES 16
 
 typedef struct {
     int32_t op;
@@ -105,7 +113,7 @@ typedef struct {
     int32_t n_prologue;     /* TinaInstr slots of the prologue program (after brdf, ambient, emission in code[]) */
     int32_t prologue_form;  /* 0: interpret it; 1: it is the 24-slot prologue of tina.PBR with a textured base colour
                              * (TEXTURE -> r0, Fresnel -> r1, diffuse -> r2, ambient -> r3, emission -> r4): run as straight-line code */
-    int32_t pad_[2];
+    int32_t pad_[2];        /* (prologue_form 2: three-address form, see TINA_OP3) */
     TinaInstr code[TINA_MAX_INSTR];
 } TinaMaterial;
 

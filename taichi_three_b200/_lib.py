@@ -15,6 +15,8 @@ TINA_MAX_LIGHTS, TINA_MAX_INSTR, TINA_MAX_TEX = 16, 96, 4
 (OP_CONST, OP_INPUT, OP_TEXTURE, OP_FRESNEL, OP_LAMBERT, OP_PHONG, OP_COOK, OP_MIX, OP_MUL,
  OP_ADD, OP_REG, OP_STORE) = range(12)
 TINA_MAX_REGS = 8
+OP3 = 0x100  # three-address prologue form (include/tina_b200.h)
+TINA_VM_VALUES = 16
 (SINK_CONST, SINK_POSITION, SINK_DEPTH, SINK_NORMAL, SINK_VIEWNORMAL, SINK_TEXCOORD, SINK_COLOR, SINK_CHESSBOARD,
  SINK_VIEWDIR, SINK_SIMPLE) = range(10)
 

@@ -212,6 +212,59 @@ __device__ V3 run_program(const TinaMaterial &m, int begin, int n, const ShadeIn
     return sp > 0 ? st[sp - 1] : v3(0.f, 0.f, 0.f);
 }
 
+// TinaMaterial.prologue_form == 2: the prologue in three-address form (include/tina_b200.h, TINA_OP3): one interpreter
+// step per operation, sources are value registers, shading inputs or inline constants.  Same operations on the same
+// values as run_program.
+__device__ void run_prologue3(const TinaMaterial &m, int begin, int n, const ShadeIn &in, V3 *vals) {
+    int pc = begin;
+    const int end = begin + n;
+    while (pc < end) {
+        const TinaInstr &I = m.code[pc++];
+        const unsigned a = (unsigned)I.arg;
+        V3 s[3];
+        const int op = I.op & 0xff;
+        const int ns = op == TINA_OP_TEXTURE || op == TINA_OP_REG ? 1 : (op == TINA_OP_MUL || op == TINA_OP_ADD ? 2 : 3);
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            if (k < ns) {
+                const unsigned code = (a >> (8 + 8 * k)) & 0xffu;
+                if (code < TINA_VM_VALUES) s[k] = vals[code];
+                else if (code < TINA_VM_VALUES + 4) s[k] = code == 16 ? in.pos : code == 17 ? in.color : code == 18 ? in.normal : in.texcoord;
+                else {
+                    const TinaInstr &C = m.code[pc++];
+                    s[k] = v3(C.c[0], C.c[1], C.c[2]);
+                }
+            }
+        }
+        V3 r;
+        switch (op) {
+        case TINA_OP_TEXTURE: {
+            const int t = (int)I.c[0];
+            r = tex_sample(m.tex[t], m.tex_w[t], m.tex_h[t], m.tex_c[t], s[0].x, s[0].y);
+            break;
+        }
+        case TINA_OP_FRESNEL: // material.py:69-83; sources in push order: metallic, albedo, specular
+            r.x = s[0].x * s[1].x + (1.0f - s[0].x) * 0.16f * (s[2].x * s[2].x);
+            r.y = s[0].y * s[1].y + (1.0f - s[0].y) * 0.16f * (s[2].y * s[2].y);
+            r.z = s[0].z * s[1].z + (1.0f - s[0].z) * 0.16f * (s[2].z * s[2].z);
+            break;
+        case TINA_OP_MIX: // push order: factor, a, b
+            r = op_mix(s[0], s[1], s[2]);
+            break;
+        case TINA_OP_MUL:
+            r = v3(s[0].x * s[1].x, s[0].y * s[1].y, s[0].z * s[1].z);
+            break;
+        case TINA_OP_ADD:
+            r = v3(s[0].x + s[1].x, s[0].y + s[1].y, s[0].z + s[1].z);
+            break;
+        default: // TINA_OP_REG: copy
+            r = s[0];
+            break;
+        }
+        vals[a & (TINA_VM_VALUES - 1)] = r;
+    }
+}
+
 // TinaMaterial.prologue_form == 1: the prologue of tina.PBR with a textured base colour (matr/material.py:701-706 after
 // the host's folding / hoisting), slot layout in material.py:_PBR_TEX_PROLOGUE.  The same operations in the same order
 // as interpreting those 24 slots -- without 24 interpreter dispatches and their local-memory stack traffic.
@@ -401,7 +454,7 @@ __device__ __forceinline__ V3 const_operand(const TinaMaterial &m, int i) { retu
 template <int KIND, bool FAST = false, bool LEANOPS = false>
 __device__ __forceinline__ V3 light_pixel(const ShadeIn &in, V3 viewdir, const TinaMaterial &mat, const TinaLighting &L) {
     V3 res = v3(0.f, 0.f, 0.f);
-    V3 regs[LEANOPS ? 1 : TINA_MAX_REGS];
+    V3 regs[LEANOPS ? 1 : TINA_VM_VALUES];
     if (LEANOPS) {
         if (mat.n_emission) res = const_operand(mat, mat.n_brdf + mat.n_ambient);
         if (mat.n_ambient) {
@@ -412,6 +465,7 @@ __device__ __forceinline__ V3 light_pixel(const ShadeIn &in, V3 viewdir, const T
         if (mat.n_prologue) { // light-independent sub-expressions (texture samples, Fresnel factors ...), once per pixel
             const V3 zero = v3(0.f, 0.f, 0.f);
             if (mat.prologue_form == 1) prologue_pbr_textured(mat, mat.n_brdf + mat.n_ambient + mat.n_emission, in, regs);
+            else if (mat.prologue_form == 2) run_prologue3(mat, mat.n_brdf + mat.n_ambient + mat.n_emission, mat.n_prologue, in, regs);
             else run_program(mat, mat.n_brdf + mat.n_ambient + mat.n_emission, mat.n_prologue, in, zero, zero, zero, regs);
         }
         V3 em = run_or_const(mat, mat.n_brdf + mat.n_ambient, mat.n_emission, in, regs);

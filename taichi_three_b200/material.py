@@ -482,6 +482,60 @@ def param_signature(material):
     return tuple(p._value.tobytes() for p in params)
 
 
+def prologue_three_address(pro):
+    """Postfix prologue -> three-address form (include/tina_b200.h, TINA_OP3): [(op, arg, c), ...] slots.
+    Leaves (CONST / INPUT / REG) become source codes of the operation that consumes them, results go to the register
+    a following STORE names or to a temporary (8..15).  Returns None when the program does not fit (then the postfix
+    form is interpreted)."""
+    out = []
+    stack = []     # operand descriptors: ('r', idx) | ('i', k) | ('c', (x, y, z))
+    free_tmp = list(range(_lib.TINA_VM_VALUES - 1, _lib.TINA_MAX_REGS - 1, -1))
+    last_op_slot = None  # index in `out` of the header that produced the value on top of the stack (if a temporary)
+
+    def release(d):
+        if d[0] == 'r' and d[1] >= _lib.TINA_MAX_REGS:
+            free_tmp.append(d[1])
+
+    def src_code(d):
+        return d[1] if d[0] == 'r' else 16 + d[1] if d[0] == 'i' else 255
+
+    for op, arg, c in pro:
+        if op in (_lib.OP_CONST, _lib.OP_INPUT, _lib.OP_REG, _lib.OP_LAMBERT):
+            stack.append(('c', tuple(c)) if op == _lib.OP_CONST else ('i', arg) if op == _lib.OP_INPUT else
+                         ('r', arg) if op == _lib.OP_REG else ('c', (_INV_PI,) * 3))
+            last_op_slot = None
+        elif op == _lib.OP_STORE:
+            top = stack.pop()
+            if last_op_slot is not None and top[0] == 'r' and top[1] >= _lib.TINA_MAX_REGS:
+                o, a, cc = out[last_op_slot]
+                out[last_op_slot] = (o, (a & ~0xff) | arg, cc)  # retarget the producing operation
+                release(top)
+            else:
+                out.append((_lib.OP3 | _lib.OP_REG, arg | src_code(top) << 8, (0.0, 0.0, 0.0)))
+                if top[0] == 'c':
+                    out.append((_lib.OP_CONST, 0, top[1]))
+            last_op_slot = None
+        elif op in (_lib.OP_TEXTURE, _lib.OP_FRESNEL, _lib.OP_MIX, _lib.OP_MUL, _lib.OP_ADD):
+            n = _arity(op)
+            srcs = stack[len(stack) - n:]
+            del stack[len(stack) - n:]
+            for d in srcs:
+                release(d)
+            if not free_tmp:
+                return None
+            dst = free_tmp.pop()
+            a = dst
+            for k, d in enumerate(srcs):
+                a |= src_code(d) << (8 + 8 * k)
+            last_op_slot = len(out)
+            out.append((_lib.OP3 | op, a, (float(arg), 0.0, 0.0)))
+            out += [(_lib.OP_CONST, 0, d[1]) for d in srcs if d[0] == 'c']
+            stack.append(('r', dst))
+        else:
+            return None  # light-dependent ops never reach the prologue
+    return out if not stack else None
+
+
 # prologue of tina.PBR(basecolor=Texture(...)) with constant metallic / roughness / specular after folding, CSE and
 # hoisting: (op, arg) per slot, None = any constant.  The device runs this shape as straight-line code.
 _PBR_TEX_PROLOGUE = [(_lib.OP_INPUT, 3), (_lib.OP_TEXTURE, None), (_lib.OP_STORE, 0),
@@ -519,8 +573,12 @@ def material_struct(material, device, fold=True, color_is_one=True):
     brdf, amb, emi, pro, textures = compile_material(material, fold, color_is_one)
     m = _lib.TinaMaterial()
     m.n_brdf, m.n_ambient, m.n_emission, m.ntex = len(brdf), len(amb), len(emi), len(textures)
-    m.n_prologue = len(pro)
     m.prologue_form = prologue_form(pro)
+    if pro and m.prologue_form == 0:  # any other prologue: three-address form, a third of the interpreter steps
+        pro3 = prologue_three_address(pro)
+        if pro3 is not None and len(brdf) + len(amb) + len(emi) + len(pro3) <= _lib.TINA_MAX_INSTR:
+            pro, m.prologue_form = pro3, 2
+    m.n_prologue = len(pro)
     keep = []
     for i, t in enumerate(textures):
         d = t.device_tensor(device)
