@@ -58,6 +58,15 @@ __device__ V3 tex_sample(const float *__restrict__ tex, int w, int h, int c, flo
     int i0 = min(max(I0, 0), w - 1), j0 = min(max(I1, 0), h - 1);
     int i1 = min(max(I0 + 1, 0), w - 1), j1 = min(max(I1 + 1, 0), h - 1);
     float o[3];
+    if (c == 4 && (((uintptr_t)tex) & 15) == 0) { // RGBA texels (the host pads RGB images): one 128-bit load per texel
+        const float4 *t4 = reinterpret_cast<const float4 *>(tex);
+        const float4 f11 = __ldg(t4 + (long long)i1 * h + j1), f10 = __ldg(t4 + (long long)i1 * h + j0);
+        const float4 f00 = __ldg(t4 + (long long)i0 * h + j0), f01 = __ldg(t4 + (long long)i0 * h + j1);
+        o[0] = ((f11.x * x0 * x1 + f10.x * x0 * y1) + f00.x * y0 * y1) + f01.x * y0 * x1;
+        o[1] = ((f11.y * x0 * x1 + f10.y * x0 * y1) + f00.y * y0 * y1) + f01.y * y0 * x1;
+        o[2] = ((f11.z * x0 * x1 + f10.z * x0 * y1) + f00.z * y0 * y1) + f01.z * y0 * x1;
+        return v3(o[0], o[1], o[2]);
+    }
 #pragma unroll
     for (int k = 0; k < 3; k++) {
         int kk = c == 1 ? 0 : k;

@@ -114,7 +114,10 @@ class Texture(Node):
     def device_tensor(self, device):
         import torch
         if self._device is None or self._device.device != device:
-            self._device = torch.as_tensor(self.image).to(device).contiguous()
+            t = torch.as_tensor(self.image).to(device)
+            if t.dim() == 3 and t.shape[2] == 3:  # RGB -> RGBA texels: the sampler reads one 128-bit word per texel
+                t = torch.cat([t, torch.zeros_like(t[..., :1])], dim=2)
+            self._device = t.contiguous()
         return self._device
 
 
