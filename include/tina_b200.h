@@ -113,7 +113,8 @@ typedef struct {
     int32_t n_prologue;     /* TinaInstr slots of the prologue program (after brdf, ambient, emission in code[]) */
     int32_t prologue_form;  /* 0: interpret it; 1: it is the 24-slot prologue of tina.PBR with a textured base colour
                              * (TEXTURE -> r0, Fresnel -> r1, diffuse -> r2, ambient -> r3, emission -> r4): run as straight-line code */
-    int32_t pad_[2];        /* (prologue_form 2: three-address form, see TINA_OP3) */
+    int32_t pad_[2];        /* (prologue_form 2: three-address form, see TINA_OP3; 3 / 4: the 19- / 11-slot prologues of
+                             * tina.Classic / tina.Diffuse with a textured colour, straight-line code as well) */
     TinaInstr code[TINA_MAX_INSTR];
 } TinaMaterial;
 

@@ -293,6 +293,25 @@ __device__ __forceinline__ void prologue_pbr_textured(const TinaMaterial &m, int
     regs[4] = op_mix(fr, v3(base.x * k19.x, base.y * k19.y, base.z * k19.z), C(21));
 }
 
+// prologue_form 3 / 4: tina.Classic / tina.Diffuse with a textured colour (material.py:_CLASSIC_TEX_PROLOGUE,
+// _DIFFUSE_TEX_PROLOGUE), same operations in the same order as interpreting the slots
+__device__ __forceinline__ void prologue_classic_textured(const TinaMaterial &m, int b, const ShadeIn &in, V3 *regs, bool classic) {
+    auto C = [&](int i) { return v3(m.code[b + i].c[0], m.code[b + i].c[1], m.code[b + i].c[2]); };
+    const int t = m.code[b + 1].arg;
+    const V3 base = tex_sample(m.tex[t], m.tex_w[t], m.tex_h[t], m.tex_c[t], in.texcoord.x, in.texcoord.y);
+    const V3 k4 = C(4);
+    regs[0] = base;
+    regs[1] = v3(base.x * k4.x, base.y * k4.y, base.z * k4.z);
+    if (classic) {
+        const V3 k14 = C(14);
+        regs[2] = op_mix(C(7), base, C(9));
+        regs[3] = op_mix(C(12), v3(base.x * k14.x, base.y * k14.y, base.z * k14.z), C(16));
+    } else {
+        const V3 k8 = C(8);
+        regs[2] = v3(base.x * k8.x, base.y * k8.y, base.z * k8.z);
+    }
+}
+
 // operand i of a specialised brdf shape: a constant or a prologue register
 __device__ __forceinline__ V3 operand(const TinaMaterial &m, int i, const V3 *regs) {
     if (m.code[i].op == TINA_OP_REG) return regs[m.code[i].arg & (TINA_MAX_REGS - 1)];
@@ -474,6 +493,7 @@ __device__ __forceinline__ V3 light_pixel(const ShadeIn &in, V3 viewdir, const T
         if (mat.n_prologue) { // light-independent sub-expressions (texture samples, Fresnel factors ...), once per pixel
             const V3 zero = v3(0.f, 0.f, 0.f);
             if (mat.prologue_form == 1) prologue_pbr_textured(mat, mat.n_brdf + mat.n_ambient + mat.n_emission, in, regs);
+            else if (mat.prologue_form >= 3) prologue_classic_textured(mat, mat.n_brdf + mat.n_ambient + mat.n_emission, in, regs, mat.prologue_form == 3);
             else if (mat.prologue_form == 2) run_prologue3(mat, mat.n_brdf + mat.n_ambient + mat.n_emission, mat.n_prologue, in, regs);
             else run_program(mat, mat.n_brdf + mat.n_ambient + mat.n_emission, mat.n_prologue, in, zero, zero, zero, regs);
         }

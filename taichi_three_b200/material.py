@@ -549,14 +549,26 @@ _PBR_TEX_PROLOGUE = [(_lib.OP_INPUT, 3), (_lib.OP_TEXTURE, None), (_lib.OP_STORE
                      (_lib.OP_MIX, None), (_lib.OP_STORE, 4)]
 
 
+# tina.Classic(color=Texture(...)): r0 = texel, r1 = r0 * c4, r2 = mix(c7, r0, c9), r3 = mix(c12, r0 * c14, c16)
+_CLASSIC_TEX_PROLOGUE = [(_lib.OP_INPUT, 3), (_lib.OP_TEXTURE, None), (_lib.OP_STORE, 0),
+                         (_lib.OP_REG, 0), (_lib.OP_CONST, None), (_lib.OP_MUL, None), (_lib.OP_STORE, 1),
+                         (_lib.OP_CONST, None), (_lib.OP_REG, 0), (_lib.OP_CONST, None), (_lib.OP_MIX, None), (_lib.OP_STORE, 2),
+                         (_lib.OP_CONST, None), (_lib.OP_REG, 0), (_lib.OP_CONST, None), (_lib.OP_MUL, None), (_lib.OP_CONST, None),
+                         (_lib.OP_MIX, None), (_lib.OP_STORE, 3)]
+# tina.Diffuse(color=Texture(...)): r0 = texel, r1 = r0 * c4, r2 = r0 * c8
+_DIFFUSE_TEX_PROLOGUE = [(_lib.OP_INPUT, 3), (_lib.OP_TEXTURE, None), (_lib.OP_STORE, 0),
+                         (_lib.OP_REG, 0), (_lib.OP_CONST, None), (_lib.OP_MUL, None), (_lib.OP_STORE, 1),
+                         (_lib.OP_REG, 0), (_lib.OP_CONST, None), (_lib.OP_MUL, None), (_lib.OP_STORE, 2)]
+_PROLOGUE_SHAPES = {1: _PBR_TEX_PROLOGUE, 3: _CLASSIC_TEX_PROLOGUE, 4: _DIFFUSE_TEX_PROLOGUE}
+
+
 def prologue_form(pro):
-    """1 if `pro` is the textured-PBR prologue shape (include/tina_b200.h, TinaMaterial.prologue_form), else 0."""
-    if len(pro) != len(_PBR_TEX_PROLOGUE):
-        return 0
-    for (op, arg, _), (top, targ) in zip(pro, _PBR_TEX_PROLOGUE):
-        if op != top or (targ is not None and arg != targ):
-            return 0
-    return 1
+    """TinaMaterial.prologue_form of a postfix prologue: 1 / 3 / 4 = the shape of tina.PBR / Classic / Diffuse with a
+    textured colour (straight-line device code), else 0 (include/tina_b200.h)."""
+    for form, shape in _PROLOGUE_SHAPES.items():
+        if len(pro) == len(shape) and all(op == top and (targ is None or arg == targ) for (op, arg, _), (top, targ) in zip(pro, shape)):
+            return form
+    return 0
 
 
 def compile_material(material, fold=True, color_is_one=True):
