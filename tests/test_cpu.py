@@ -168,3 +168,91 @@ def test_material_compile_shapes(tina):
     assert ops(p).count(L.OP_TEXTURE) == 1 and ops(a) == [L.OP_REG] and len(tex) == 1
     b, a, e, p, _ = compile_material(tina.Classic(color=tina.Texture(img)))
     assert ops(b) == [L.OP_CONST, L.OP_REG, L.OP_CONST, L.OP_PHONG, L.OP_MIX] and ops(p).count(L.OP_TEXTURE) == 1
+
+
+def test_three_address_prologue_equals_postfix(tina):
+    """material.prologue_three_address (TinaMaterial.prologue_form 2): evaluating the three-address program gives the
+    registers of the postfix prologue bit for bit (numpy f32 evaluators of both forms; the texture is a stub)."""
+    from taichi_three_b200 import _lib, material as M
+    F = np.float32
+    img = np.random.default_rng(0).random((5, 4, 3)).astype(F)
+
+    def tex(uv):
+        return (uv * F(0.37) + F(0.11)).astype(F)
+
+    def fres(me, al, sp):
+        return me * al + (F(1) - me) * F(0.16) * (sp * sp)
+
+    def mix(f, a, b):
+        return (F(1) - f) * a + f * b
+
+    def run_postfix(pro, inputs):
+        st, regs = [], {}
+        for op, arg, c in pro:
+            if op == _lib.OP_CONST:
+                st.append(np.asarray(c, F))
+            elif op == _lib.OP_INPUT:
+                st.append(inputs[arg])
+            elif op == _lib.OP_REG:
+                st.append(regs[arg])
+            elif op == _lib.OP_STORE:
+                regs[arg] = st.pop()
+            elif op == _lib.OP_TEXTURE:
+                st.append(tex(st.pop()))
+            elif op == _lib.OP_FRESNEL:
+                sp, al, me = st.pop(), st.pop(), st.pop()
+                st.append(fres(me, al, sp))
+            elif op == _lib.OP_MIX:
+                b, a, f = st.pop(), st.pop(), st.pop()
+                st.append(mix(f, a, b))
+            elif op == _lib.OP_MUL:
+                w, f = st.pop(), st.pop()
+                st.append(f * w)
+            elif op == _lib.OP_ADD:
+                b, a = st.pop(), st.pop()
+                st.append(a + b)
+            else:
+                raise AssertionError(op)
+        assert not st
+        return regs
+
+    def run_three(pro3, inputs):
+        vals, pc = {}, 0
+        while pc < len(pro3):
+            op, a, c = pro3[pc]
+            pc += 1
+            assert op & _lib.OP3
+            op &= 0xff
+            ns = 1 if op in (_lib.OP_TEXTURE, _lib.OP_REG) else 2 if op in (_lib.OP_MUL, _lib.OP_ADD) else 3
+            s = []
+            for k in range(ns):
+                code = (a >> (8 + 8 * k)) & 0xff
+                if code < 16:
+                    s.append(vals[code])
+                elif code < 20:
+                    s.append(inputs[code - 16])
+                else:
+                    assert pro3[pc][0] == _lib.OP_CONST
+                    s.append(np.asarray(pro3[pc][2], F))
+                    pc += 1
+            r = (tex(s[0]) if op == _lib.OP_TEXTURE else fres(*s) if op == _lib.OP_FRESNEL else mix(*s) if op == _lib.OP_MIX else
+                 s[0] * s[1] if op == _lib.OP_MUL else s[0] + s[1] if op == _lib.OP_ADD else s[0])
+            vals[a & 0xff] = r
+        return vals
+
+    inputs = [np.asarray(v, F) for v in ([0.1, 0.2, 0.3], [1, 1, 1], [0, 0.6, 0.8], [0.25, 0.75, 0])]
+    mats = [tina.PBR(basecolor=tina.Texture(img), metallic=0.3, roughness=0.4), tina.Classic(color=tina.Texture(img)),
+            tina.Diffuse(color=tina.Texture(img)),
+            tina.Lambert() * tina.Texture(img) + tina.Phong(shineness=16) * tina.Texture(img) + tina.Emission() * 0.1,
+            tina.PBR(basecolor=tina.Texture(img), metallic=tina.Texture(img), roughness=0.4)]
+    forms = []
+    for mat in mats:
+        b, a, e, pro, _ = M.compile_material(mat)
+        assert pro
+        forms.append(M.prologue_form(pro))
+        pro3 = M.prologue_three_address(pro)
+        assert pro3 is not None and sum(1 for o, _, _ in pro3 if o & _lib.OP3) < len(pro) / 2
+        want, got = run_postfix(pro, inputs), run_three(pro3, inputs)
+        for r, v in want.items():
+            assert np.array_equal(got[r], v), (mat, r)
+    assert forms[:4] == [1, 3, 4, 0]
