@@ -135,9 +135,15 @@ int tina_engine_destroy(TinaEngine *e);
 int tina_engine_set_camera(TinaEngine *e, const float *W2V_host, const float *V2W_host);
 /* engine.py:31-39 */
 int tina_engine_set_bias(TinaEngine *e, float bx, float by);
-/* engine.py:68-70: depth := 2**30, winner := none, face_base := 0 */
+/* engine.py:68-70: depth := 2**30, winner := none, face_base := 0.  The device-side clear is deferred to the next
+ * library call that touches the keys (render_occup of a MeshGrid / MeshModel folds it into its vertex-stage launch);
+ * host-side state changes at once.  Nothing is deferred under stream capture. */
 int tina_engine_clear_depth(TinaEngine *e, void *stream);
-/* int64 keys[W*H]; the high words are Engine.depth viewed with stride 2 */
+/* run a deferred clear now (call before reading / writing the memory behind tina_engine_keys directly) */
+int tina_engine_flush(TinaEngine *e, void *stream);
+/* on = 0: tina_engine_clear_depth clears immediately (default 1 = deferred) */
+int tina_engine_set_lazy_clear(TinaEngine *e, int on);
+/* int64 keys[W*H]; the high words are Engine.depth viewed with stride 2 (see tina_engine_flush) */
 int tina_engine_keys(TinaEngine *e, int64_t **keys);
 /* materialise Engine.depth as a dense int32[W*H] */
 int tina_engine_depth(TinaEngine *e, int32_t *depth, void *stream);
@@ -245,13 +251,17 @@ int tina_raster_buffers(TinaRaster *r, const float **verts, const float **norms,
  *      Applies to constant-brdf and Lambert+Phong (constant shineness <= 64) materials; Cook-Torrance and
  *      interpreted programs always shade exactly;
  *      0 = every shading op in the reference's order with IEEE division/sqrt,
- * 14 = lean shading kernels (default 1): with fast shading, Diffuse / Classic materials whose parameters are all
- *      constants on untextured rasters run kernels with compile-time raster flags and no operand tests */
+ * 14 = lean kernels (default 1): the default raster options / plain sources as compile-time constants in the
+ *      rasteriser; with fast shading, Diffuse / Classic materials whose parameters are all constants on untextured
+ *      rasters run shading kernels with compile-time raster flags and no operand tests,
+ * 15 = indexed sources: mark every vertex record "not tame", so that every face takes the rasteriser's general
+ *      path (float bounding box, x86 conversions, no tightening) instead of the per-vertex integer bounds */
 int tina_raster_set_tuning(TinaRaster *r, int which, int value);
 /* counters of the last render_occup (synchronises): faces culled, clipped, per-thread,
  * per-warp, queued for the tile path, tile-list entries */
 int tina_raster_stats(TinaRaster *r, int64_t *out6_host);
-/* ms of the last launch of: [0] k_raster_faces, [1] k_vtx_clip (indexed sources only), [3] k_large_path,
+/* ms of the last launch of: [0] k_raster_faces / k_raster_indexed, [1] k_frame_prologue (indexed sources only:
+ * vertex records + the deferred key clear), [3] k_large_path,
  * [4] k_render_color ([2] unused; -1 = never recorded); needs tuning knob 4; synchronises on the events */
 int tina_raster_kernel_times(TinaRaster *r, float *ms5_host);
 

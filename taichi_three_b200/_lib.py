@@ -55,6 +55,8 @@ SIGNATURES = {
     'tina_engine_set_camera': (_i, [_vp, _fp, _fp]),
     'tina_engine_set_bias': (_i, [_vp, _f, _f]),
     'tina_engine_clear_depth': (_i, [_vp, _vp]),
+    'tina_engine_flush': (_i, [_vp, _vp]),
+    'tina_engine_set_lazy_clear': (_i, [_vp, _i]),
     'tina_engine_keys': (_i, [_vp, C.POINTER(_vp)]),
     'tina_engine_depth': (_i, [_vp, _vp, _vp]),
     'tina_engine_set_face_base': (_i, [_vp, _u32]),

@@ -78,7 +78,9 @@ struct Src {
     const float *vpos;      // world positions per unique vertex
     const float *vnrm;      // world normals per unique normal
     const float *vtex;      // model: texture coordinates per unique vt
-    const float4 *vclip;    // (x/w, y/w, z_clip, w_clip) per unique vertex
+    // per-unique-vertex records written by the vertex stage (k_frame_prologue, raster_indexed.cuh):
+    const float4 *recA;     // (viewport x, viewport y, z/w, 1/w): engine.py:52-53,60-61 + triangle.py:113
+    const uint4 *recB;      // (candidate lower bounds x|y<<16, upper bounds x|y<<16, bits of x/w, bits of y/w)
 };
 
 // corner k of output face n -> vertex / texcoord / normal ids (mesh/grid.py:45-58, mesh/model.py:56-73,
@@ -226,7 +228,10 @@ __device__ __forceinline__ void face_phase_b(const FaceA &f, Setup &s) {
 #define HQ_CAP 64 /* per-warp deferred-hit queue entries */
 // Append this warp's large faces to the tile-path queue (warp-aggregated), with their finished edge setups, and
 // add the warp's stats.  Called by whole warps.
-__device__ __forceinline__ void queue_large_faces(const FaceA &f, bool big, bool queued, bool surv, int rc, unsigned gface,
+// `mk(Setup&)` computes the face's finished edge setup (only evaluated for queued faces).
+template <typename MakeSetup>
+__device__ __forceinline__ void queue_large_faces(int botx, int boty, int topx, int topy, MakeSetup mk, bool big, bool queued,
+                                                  bool surv, int rc, unsigned gface,
                                                   unsigned lane, uint4 *__restrict__ queue, unsigned *__restrict__ counters,
                                                   unsigned queue_cap, float4 *__restrict__ qsetup, unsigned qsetup_cap,
                                                   int inline_large, int collect_stats) {
@@ -244,11 +249,11 @@ __device__ __forceinline__ void queue_large_faces(const FaceA &f, bool big, bool
             if (queued) {
                 unsigned my = slot + __popc(qm & ((1u << lane) - 1u));
                 if (my < queue_cap)
-                    queue[my] = make_uint4(gface, (unsigned)f.botx | ((unsigned)f.boty << 16),
-                                           (unsigned)f.topx | ((unsigned)f.topy << 16), 0u);
+                    queue[my] = make_uint4(gface, (unsigned)botx | ((unsigned)boty << 16),
+                                           (unsigned)topx | ((unsigned)topy << 16), 0u);
                 if (my < qsetup_cap) { // finished edge setup, so that no tile has to redo its 16 divisions
                     Setup q;
-                    face_phase_b(f, q);
+                    mk(q);
                     float4 *o = qsetup + (size_t)my * 4;
                     o[0] = make_float4(q.bcnx, q.bcny, q.canx, q.cany);
                     o[1] = make_float4(q.bx, q.by, q.cx, q.cy);
@@ -273,15 +278,21 @@ __device__ __forceinline__ void queue_large_faces(const FaceA &f, bool big, bool
 // Phase B walk of one warp's survivors (lane = one face: setup s, candidate range f.xlo..f.yhi, cnt candidates,
 // id = global face id + 1).  `wk` is the warp's WALK_WORDS-word scratch region in shared memory (free for its use),
 // `hq` the warp's deferred-hit queue.  Called by whole warps.
+// SHARED = false: per-lane walk only (no scratch needed: wk / hq may be null).
+template <bool SHARED = true>
 __device__ __forceinline__ void walk_candidates(const FaceA &f, const Setup &s, unsigned id, int cnt, int col, unsigned lane,
                                                 const Cam &cam, long long *__restrict__ keys,
                                                 unsigned char *__restrict__ blkflags, unsigned char flagval, int precheck,
                                                 int balance, float *wk, unsigned (*hq)[2]) {
     const float bxs = cam.bias[0], bys = cam.bias[1];
     // How uneven is this warp?  M = longest lane, T = total candidate pixels.
-    const int M = __reduce_max_sync(0xffffffffu, cnt), T = __reduce_add_sync(0xffffffffu, cnt); // REDUX: one instruction each
-    const bool shared_walk = (balance == 2) || (balance == 1 && (long long)M * 40 > (long long)((T + 31) >> 5) * 75 + 150);
-    if (!shared_walk || T > WALK_MAX_T) {
+    int M = 0, T = 0;
+    bool shared_walk = false;
+    if (SHARED) {
+        M = __reduce_max_sync(0xffffffffu, cnt), T = __reduce_add_sync(0xffffffffu, cnt); // REDUX: one instruction each
+        shared_walk = (balance == 2) || (balance == 1 && (long long)M * 40 > (long long)((T + 31) >> 5) * 75 + 150);
+    }
+    if (!SHARED || !shared_walk || T > WALK_MAX_T) {
         // per-lane walk of the candidate range, x-outer / y-inner like triangle.py:114; the inner loop
         // only does the cheap exact reject, candidates fall out to the division + atomic part
         int x = f.xlo, y = f.ylo;
@@ -407,20 +418,20 @@ __device__ __forceinline__ void walk_candidates(const FaceA &f, const Setup &s, 
 }
 
 // stats layout in counters[]: [4] culled [5] clipped [6] survivors (phase B) [7] queued
-// LEAN = 0: every option read at run time.  LEAN != 0: the default configuration as compile-time constants --
-// culling + clipping on, tightening on, no key pre-read, no stats; 1 / 2 = indexed source of kind grid / model with
-// mode 0 (no NoCulling / flip wrappers), 3 = expanded arrays -- which removes the option tests from the per-face
-// path (C2: K1 43.6 -> 39.0 us).
-template <bool IDX, int LEAN = 0>
-// (register budget: 40 for the indexed variants -- C2 is fastest there -- and 41-42 for the expanded-array ones, whose
-// shared walk then keeps its shared-memory addresses in registers: C3 1.67 -> 1.57 ms; six CTAs per SM either way)
-__global__ void __launch_bounds__(K1_THREADS, IDX ? 6 : 5)
+// LEAN = 0: every option read at run time.  LEAN = 3: the default configuration as compile-time constants --
+// culling + clipping on, tightening on, no key pre-read, no stats -- which removes the option tests from the
+// per-face path.
+// This kernel serves the expanded [N,3,3] arrays (SimpleMesh, soups); indexed sources (MeshGrid / MeshModel) have
+// their own kernel on per-vertex records (raster_indexed.cuh).
+template <int LEAN = 0>
+// (register budget 41-42: the shared walk then keeps its shared-memory addresses in registers: C3 1.67 -> 1.57 ms)
+__global__ void __launch_bounds__(K1_THREADS, 5)
 k_raster_faces(const float *__restrict__ verts, long long nfaces, const __grid_constant__ Cam cam, uint32_t flags_rt,
                unsigned base, long long *__restrict__ keys, uint4 *__restrict__ queue, unsigned *__restrict__ counters,
                unsigned queue_cap, int tiny_max, int tighten_rt, int precheck_rt, int balance, int collect_stats_rt,
                const __grid_constant__ Src S, unsigned char *__restrict__ blkflags, unsigned *__restrict__ next_counters,
                int inline_large, float4 *__restrict__ qsetup, unsigned qsetup_cap, unsigned char flagval) {
-    static_assert(IDX ? LEAN <= 2 : (LEAN == 0 || LEAN == 3), "lean variants: 1 grid, 2 model (indexed), 3 expanded arrays");
+    static_assert(LEAN == 0 || LEAN == 3, "lean variant: 3 = expanded arrays with the default options");
     const uint32_t flags = LEAN ? (uint32_t)(TINA_CULLING | TINA_CLIPPING) : flags_rt;
     const int tighten = LEAN ? 1 : tighten_rt, precheck = LEAN ? 0 : precheck_rt, collect_stats = LEAN ? 0 : collect_stats_rt;
     // staging of the CTA's vertices, later reused for the compacted survivor records (SoA)
@@ -442,10 +453,8 @@ k_raster_faces(const float *__restrict__ verts, long long nfaces, const __grid_c
     const int nfl = n * 9;
     if (tid == 0) s_nsurv = 0;
     // the CTA's 256 x 36 B of vertices arrive with ONE bulk-copy instruction (TMA, UBLKCP)
-    const bool bulk = !IDX && ((((uintptr_t)src) & 15) == 0) && ((nfl & 3) == 0);
-    if (IDX) {
-        // indexed source: the three corners come from the per-vertex clip cache, nothing to stage
-    } else if (bulk) {
+    const bool bulk = ((((uintptr_t)src) & 15) == 0) && ((nfl & 3) == 0);
+    if (bulk) {
         if (tid == 0) mbar_init(&s_mbar, 1);
         __syncthreads();
         if (tid == 0) {
@@ -463,17 +472,10 @@ k_raster_faces(const float *__restrict__ verts, long long nfaces, const __grid_c
     int rc = 3; // 3 = inactive lane
     int cnt = 0, refarea = 0;
     if (tid < n) {
-        if (IDX) {
-            int iv[3], it[3], in_[3], gi[3], gj[3];
-            bool neg;
-            corner_ids<(LEAN == 1 || LEAN == 2) ? LEAN : 0>(S, f0 + tid, iv, it, in_, gi, gj, neg);
-            rc = face_phase_a_clip(__ldg(S.vclip + iv[0]), __ldg(S.vclip + iv[1]), __ldg(S.vclip + iv[2]), cam, flags, tighten, f);
-        } else {
-            float v[9];
+        float v[9];
 #pragma unroll
-            for (int k = 0; k < 9; k++) v[k] = sm[tid * 9 + k];
-            rc = face_phase_a(v, cam, flags, tighten, f);
-        }
+        for (int k = 0; k < 9; k++) v[k] = sm[tid * 9 + k];
+        rc = face_phase_a(v, cam, flags, tighten, f);
         if (rc == 0) {
             const int rw_ = f.topx - f.botx + 1, rh_ = f.topy - f.boty + 1;
             refarea = (rw_ > 0 && rh_ > 0) ? rw_ * rh_ : 0;
@@ -507,8 +509,8 @@ k_raster_faces(const float *__restrict__ verts, long long nfaces, const __grid_c
             r[14 * K1_THREADS] = __int_as_float(tid);
         }
     }
-    queue_large_faces(f, big, queued, surv, rc, (unsigned)(f0 + tid), lane, queue, counters, queue_cap, qsetup, qsetup_cap,
-                      inline_large, collect_stats);
+    queue_large_faces(f.botx, f.boty, f.topx, f.topy, [&](Setup &q) { face_phase_b(f, q); }, big, queued, surv, rc,
+                      (unsigned)(f0 + tid), lane, queue, counters, queue_cap, qsetup, qsetup_cap, inline_large, collect_stats);
     __syncthreads();
 
     // ---- phase B: dense over survivors ----

@@ -380,7 +380,7 @@ __device__ __forceinline__ void pixel_inputs(int P, unsigned f, const float *__r
         corner_ids<CK>(S, (long long)f, iv, it, in_, gi, gj, neg);
         // every gather is issued before the first use of any of them (one exposed round trip, not three);
         // the sign of a negated normal is applied after the interpolation (-(x) commutes with rounding)
-        const float4 ca = __ldg(S.vclip + iv[0]), cb = __ldg(S.vclip + iv[1]), cc = __ldg(S.vclip + iv[2]);
+        const float4 ca = __ldg(S.recA + iv[0]), cb = __ldg(S.recA + iv[1]), cc = __ldg(S.recA + iv[2]);
 #pragma unroll
         for (int k = 0; k < 3; k++) {
             const float *p = S.vpos + (long long)iv[k] * 3;
@@ -405,7 +405,7 @@ __device__ __forceinline__ void pixel_inputs(int P, unsigned f, const float *__r
                 }
             }
         }
-        setup_weights_clip(ca, cb, cc, cam, s);
+        setup_from_records(ca, cb, cc, s); // the vertex stage's viewport coordinates and 1/w: same bits as setup_weights
     } else {
         const float *v = verts + (long long)f * 9;
 #pragma unroll

@@ -133,13 +133,7 @@ __global__ void k_vtx_world(const float *__restrict__ v, long long nv, const flo
     }
 }
 
-// engine.py:52-53 per unique vertex: (x/w, y/w, z_clip, w_clip), camera-dependent => runs in render_occup
-__global__ void k_vtx_clip(const float *__restrict__ vpos, long long nv, const __grid_constant__ Cam cam,
-                           float4 *__restrict__ vclip) {
-    pdl_wait();
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < nv) vclip[t] = vertex_clip(cam, __ldg(vpos + t * 3), __ldg(vpos + t * 3 + 1), __ldg(vpos + t * 3 + 2));
-}
+// (the camera-dependent part of the vertex stage, k_frame_prologue, lives in raster_indexed.cuh)
 
 // pars/trans.py:22-31
 __global__ void k_pars_transform(const float *__restrict__ v, const float *__restrict__ sz, long long n,
@@ -164,6 +158,8 @@ struct IndexedState {
     int64_t a_nout;
     // owned per-vertex buffers
     float *vpos_w, *vnrm_w;
-    float4 *vclip;
-    int64_t vpos_cap, vnrm_cap, vclip_cap, nv, nvn;
+    float4 *recA; // per-vertex records, written by k_frame_prologue in render_occup (raster_indexed.cuh)
+    uint4 *recB;
+    int64_t vpos_cap, vnrm_cap, recA_cap, recB_cap, nv, nvn;
+    int force_general; // tuning knob 15: mark every vertex non-tame (every face takes K1's general path)
 };

@@ -37,10 +37,10 @@ class Engine:
         _lib.check(L.tina_engine_create(C.byref(h), self.device.index, self.res[0], self.res[1]))
         self._h = h
         self._clear = L.tina_engine_clear_depth
+        self._flush = L.tina_engine_flush
         kp = C.c_void_p()
         _lib.check(L.tina_engine_keys(self._h, C.byref(kp)))
-        #: int64[W, H]  key = depth << 32 | (global face id + 1)
-        self.keys = wrap_device(kp.value, self.res, torch.int64, self.device, owner=self)
+        self._keys = wrap_device(kp.value, self.res, torch.int64, self.device, owner=self)
         # engine.py:21-26
         m = np.eye(4, dtype=np.float32)
         m[2, 2] = -1
@@ -63,6 +63,15 @@ class Engine:
         _lib.check(L.tina_engine_set_camera(self._h, w2v, v2w))
         b = self.bias.to_numpy()
         _lib.check(L.tina_engine_set_bias(self._h, float(b[0]), float(b[1])))
+
+    @property
+    def keys(self):
+        """int64[W, H]  key = depth << 32 | (global face id + 1).  (clear_depth is deferred inside the library until
+        something touches the keys; handing out the tensor is such a touch.)"""
+        rc = self._flush(self._h, _stream(self.device.index))
+        if rc:
+            _lib.check(rc)
+        return self._keys
 
     @property
     def depth(self):

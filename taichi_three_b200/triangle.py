@@ -266,11 +266,11 @@ class TriangleRaster:
         """ms of the last launch of each kernel (needs set_tuning(profile=1)); -1 = not recorded."""
         out = (C.c_float * 5)()
         _lib.check(_lib.lib().tina_raster_kernel_times(self._h, out))
-        return dict(zip(('raster_faces', 'vtx_clip', 'unused2', 'large_path', 'render_color'), list(out)))
+        return dict(zip(('raster_faces', 'frame_prologue', 'unused2', 'large_path', 'render_color'), list(out)))
 
     def set_tuning(self, tiny_max=None, force_tiles=None, collect_stats=None, profile=None, tighten=None,
                    precheck=None, scan_max=None, generic_vm=None, balance=None, pdl=None, indexed=None, adaptive=None,
-                   fast_shading=None, lean_kernels=None):
+                   fast_shading=None, lean_kernels=None, force_general=None):
         """Strategy knobs (every setting produces identical ids/depth bits; only fast_shading changes colour, by
         < 1e-4): tiny_max = most candidate pixels a
         face may have to be rasterised per thread in the setup kernel (more -> tile path);
@@ -282,7 +282,8 @@ class TriangleRaster:
         indexed = per-unique-vertex stage for MeshGrid / MeshModel (takes effect at the next set_object);
         adaptive = stop launching the tile-path kernel after 8 consecutive calls that queued nothing;
         fast_shading = FMA / SFU arithmetic downstream of the (always exact) barycentric weights in render_color;
-        lean_kernels = specialised shading kernels for constant-parameter Diffuse / Classic on untextured rasters."""
+        lean_kernels = specialised shading kernels for constant-parameter Diffuse / Classic on untextured rasters;
+        force_general = indexed sources: every face takes the rasteriser's general path (no per-vertex integer bounds)."""
         L = _lib.lib()
         if tiny_max is not None:
             _lib.check(L.tina_raster_set_tuning(self._h, 0, int(tiny_max)))
@@ -293,7 +294,7 @@ class TriangleRaster:
         if profile is not None:
             _lib.check(L.tina_raster_set_tuning(self._h, 4, int(profile)))
         for which, v in ((5, tighten), (6, precheck), (7, scan_max), (8, generic_vm), (9, balance), (10, pdl), (11, indexed), (12, adaptive),
-                         (13, fast_shading), (14, lean_kernels)):
+                         (13, fast_shading), (14, lean_kernels), (15, force_general)):
             if v is not None:
                 _lib.check(L.tina_raster_set_tuning(self._h, which, int(v)))
 

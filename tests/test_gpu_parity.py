@@ -1009,3 +1009,124 @@ def test_textured_materials_all_prologue_forms(tina, O):
         scene.render()
         torch.cuda.synchronize()
         assert np.abs(scene.img.to_numpy() - ref['image']).max() <= COLOR_TOL, form
+
+
+def _edge_case_triangles(W, H):
+    tri = scenes.soup(3000, W, H, s=0.05, seed=5)
+    extra = np.array([
+        [[-9, -9, 0], [9, -9, 0], [0, 9, 0]],            # screen-filling, all vertices outside
+        [[-0.5, -0.5, 5], [0.5, -0.5, 5], [0, 0.5, 5]],  # behind the camera
+        [[-0.5, -0.5, 0], [0.5, -0.5, 4], [0, 0.5, 0]],  # crosses w = 0
+        [[0, 0, 0], [0, 0, 0], [0, 0, 0]],               # degenerate
+        [[np.nan, 0, 0], [1, 0, 0], [0, 1, 0]],          # NaN
+        [[np.inf, 0, 0], [1, 0, 0], [0, 1, 0]],          # inf
+        [[50, 50, 0], [51, 50, 0], [50, 51, 0]],         # far off-screen
+        [[0, 0, 2.9999], [0.1, 0, 2.9999], [0, 0.1, 2.9999]],  # w ~ 1e-4: huge viewport coordinates (not tame)
+        [[-1, -1, 0.5], [1, -1, 0.5], [0, 1, 0.5]],      # big, front-facing
+        [[-1, -1, 0.2], [0, 1, 0.2], [1, -1, 0.2]],      # big, back-facing
+        [[1e-3, 0, 1], [2e-3, 0, 1], [1e-3, 1e-3, 1]],   # sub-pixel
+    ], dtype=np.float32)
+    return np.ascontiguousarray(np.concatenate([extra, tri, extra[::-1]]))
+
+
+@pytest.mark.parametrize('culling,clipping', [(True, True), (True, False), (False, True), (False, False)])
+def test_indexed_records_edge_cases_and_general_path(tina, O, culling, clipping):
+    """The indexed rasteriser (k_raster_indexed) on per-vertex records: vertices behind the camera, NaN / inf,
+    w ~ 0 (huge viewport coordinates), off-screen and screen-filling faces as a MeshModel.  Ids + depth equal the
+    oracle, and the per-vertex integer bounds (record path) equal the general float-bbox path (force_general) and
+    the untightened walk bit for bit."""
+    import torch
+    W, H = 200, 136
+    view, proj = scenes.default_camera(W / H)
+    tri = _edge_case_triangles(W, H)
+    obj = {'v': tri.reshape(-1, 3), 'f': np.arange(len(tri) * 3).reshape(-1, 3)}
+    ref = None
+    keys = []
+    for tuning in (dict(), dict(force_general=1), dict(tighten=0), dict(lean_kernels=0), dict(balance=0), dict(tiny_max=4),
+                   dict(force_tiles=1)):
+        scene = tina.Scene((W, H), culling=culling, clipping=clipping)
+        scene.add_object(tina.MeshModel(obj))
+        scene.engine.set_camera(view, proj)
+        scene.triangle_raster.set_tuning(**tuning)
+        scene.render()
+        torch.cuda.synchronize()
+        if ref is None:
+            with np.errstate(all='ignore'):
+                ref = O.render_scene([(tri, None, None, tina.Diffuse())], W, H, view, proj, scene.lighting,
+                                     _flags(O, culling=culling, clipping=clipping))
+        assert np.array_equal(scene.engine.depth.to_numpy(), ref['depth']), tuning
+        assert np.array_equal(scene.triangle_raster.occup.to_numpy(), ref['occups'][-1]), tuning
+        keys.append(_keys(scene))
+    for k in keys[1:]:
+        assert np.array_equal(k, keys[0])
+    assert (ref['depth'] < 2**30).sum() > 1000
+
+
+@pytest.mark.parametrize('bias', [(0.5, 0.5), (0.123, 0.877), (0.0, 1.0), (1.5, -0.25)])
+def test_indexed_record_bounds_equal_general_path_micro_grid(tina, O, bias):
+    """Sub-pixel regime (C2's): a wavy grid at 0.3 px per face.  Per-vertex integer candidate bounds + min3 / max3
+    must select exactly the candidates of the per-face float computation (general path), for centred, jittered,
+    extreme and out-of-range sample bias (the last one disables tightening on the host)."""
+    import torch
+    n, W, H = 160, 96, 64
+    pos = scenes.wave_grid_pos(n)
+    view, proj = scenes.default_camera(W / H)
+    keys = []
+    for tuning in (dict(), dict(force_general=1), dict(tighten=0)):
+        scene = tina.Scene((W, H), smoothing=True)
+        grid = tina.MeshGrid(n)
+        grid.pos.from_numpy(pos)
+        scene.add_object(grid, tina.Classic())
+        scene.engine.set_camera(view, proj)
+        scene.engine.bias[None] = bias
+        scene.triangle_raster.set_tuning(**tuning)
+        scene.render()
+        torch.cuda.synchronize()
+        keys.append(_keys(scene))
+    assert np.array_equal(keys[0], keys[1]) and np.array_equal(keys[0], keys[2])
+    fv = O.grid_faces(pos)
+    ref = O.render_scene([(fv, O.grid_faces(O.grid_normals(pos)), None, tina.Classic())], W, H, view, proj, scene.lighting,
+                         _flags(O, smoothing=True), bias=bias)
+    d, o = keys[0] >> 32, (keys[0] & 0xffffffff).astype(np.int64) - 1
+    assert np.array_equal(d.astype(np.int32), ref['depth'])
+    assert np.array_equal(o.astype(np.int32), ref['occups'][-1])
+
+
+def test_deferred_clear_depth_semantics(tina, O):
+    """clear_depth is deferred inside the library (folded into the next render_occup of an indexed source); every
+    observable view must still see it: engine.keys / engine.depth right after the clear, a second clear, other
+    rasterisers, and an immediate clear (lazy off) must all give the same frames."""
+    import torch
+    W, H = 160, 120
+    view, proj = scenes.default_camera(W / H)
+    pos = scenes.wave_grid_pos(40)
+    scene = tina.Scene((W, H), smoothing=True)
+    grid = tina.MeshGrid(40)
+    grid.pos.from_numpy(pos)
+    scene.add_object(grid, tina.Classic())
+    scene.engine.set_camera(view, proj)
+    scene.render()
+    k1 = _keys(scene)
+    assert ((k1 & 0xffffffff) != 0).sum() > 500
+    scene.engine.clear_depth()
+    assert np.all(scene.engine.depth.to_numpy() == 2**30)          # the view flushes the pending clear
+    assert np.all((scene.engine.keys.cpu().numpy() & 0xffffffff) == 0)
+    scene.engine.clear_depth()
+    scene.engine.clear_depth()
+    scene.render()
+    assert np.array_equal(_keys(scene), k1)
+    # the expanded-array rasteriser after a deferred clear
+    scene2 = tina.Scene((W, H))
+    tri = scenes.soup(2000, W, H, s=0.03, seed=3)
+    mesh = tina.SimpleMesh()
+    mesh.set_face_verts(tri)
+    scene2.add_object(mesh)
+    scene2.engine.set_camera(view, proj)
+    scene2.render()
+    a = _keys(scene2)
+    scene2.render()
+    assert np.array_equal(_keys(scene2), a)
+    from taichi_three_b200 import _lib
+    _lib.check(_lib.lib().tina_engine_set_lazy_clear(scene2.engine._h, 0))
+    scene2.render()
+    assert np.array_equal(_keys(scene2), a)
