@@ -1130,3 +1130,36 @@ def test_deferred_clear_depth_semantics(tina, O):
     _lib.check(_lib.lib().tina_engine_set_lazy_clear(scene2.engine._h, 0))
     scene2.render()
     assert np.array_equal(_keys(scene2), a)
+
+
+@pytest.mark.parametrize('n,W,H', [(160, 96, 64), (300, 640, 360), (131, 200, 136), (5, 64, 48)])
+def test_grid_tile_rasteriser_equals_gather_kernel(tina, O, n, W, H):
+    """k_raster_grid (knob grid_tiles: independent persistent warps over row chunks staged by cp.async) must give the
+    bits of the gather kernel and of the oracle: chunks per row that divide / do not divide the row, more chunks than
+    resident warps, a grid smaller than one chunk; with and without the lean variant and culling."""
+    import torch
+    pos = scenes.wave_grid_pos(n)
+    view, proj = scenes.default_camera(W / H)
+    fv = O.grid_faces(pos)
+    for culling in (True, False):
+        keys = []
+        for tuning in (dict(), dict(grid_tiles=1), dict(grid_tiles=1, lean_kernels=0), dict(grid_tiles=1, force_general=1),
+                       dict(grid_tiles=1, tiny_max=2), dict(lean_kernels=0), dict(tiny_max=2)):
+            scene = tina.Scene((W, H), smoothing=True, culling=culling)
+            grid = tina.MeshGrid(n)
+            grid.pos.from_numpy(pos)
+            scene.add_object(grid, tina.Classic())
+            scene.engine.set_camera(view, proj)
+            scene.triangle_raster.set_tuning(**tuning)
+            scene.render()
+            scene.render()  # (second frame: the pipeline's stage / parity state starts over per launch)
+            torch.cuda.synchronize()
+            keys.append(_keys(scene))
+        for k in keys[1:]:
+            assert np.array_equal(k, keys[0])
+        ref = O.render_scene([(fv, O.grid_faces(O.grid_normals(pos)), None, tina.Classic())], W, H, view, proj, scene.lighting,
+                             _flags(O, smoothing=True, culling=culling))
+        d, o = keys[0] >> 32, (keys[0] & 0xffffffff).astype(np.int64) - 1
+        assert np.array_equal(d.astype(np.int32), ref['depth'])
+        assert np.array_equal(o.astype(np.int32), ref['occups'][-1])
+        _check_frame(scene, ref)
