@@ -45,6 +45,14 @@ def num_threads():
     return lib().orc_num_threads()
 
 
+def set_num_threads(n=None):
+    """Use n host threads (default: every core this process may run on) regardless of OMP_NUM_THREADS."""
+    if n is None:
+        n = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
+    lib().orc_set_num_threads(int(n))
+    return num_threads()
+
+
 def clear_depth(W, H):
     return np.full((W, H), 2**30, dtype=np.int32)
 
@@ -76,22 +84,21 @@ def face_setup(verts, W2V, W, H, flags=CULLING | CLIPPING):
 
 
 def _material_pod(material):
-    """the plain (unfolded, unhoisted) TinaMaterial program + host texture pointers"""
-    from taichi_three_b200 import _lib as P
-    from taichi_three_b200.material import flatten_material
-    brdf, amb, emi, textures = flatten_material(material)
-    m = P.TinaMaterial()
-    m.n_brdf, m.n_ambient, m.n_emission, m.ntex = len(brdf), len(amb), len(emi), len(textures)
-    m.n_prologue = 0  # the oracle interprets the plain, unfolded, unhoisted programs
-    for i, (op, arg, c) in enumerate(brdf + amb + emi):
-        m.code[i].op, m.code[i].arg = op, arg
-        m.code[i].c[0], m.code[i].c[1], m.code[i].c[2] = c
-    tex_arrays = [np.ascontiguousarray(t.image, dtype=np.float32) for t in textures]
-    texptrs = (C.c_void_p * max(1, len(tex_arrays)))()
-    for i, t in enumerate(tex_arrays):
-        texptrs[i] = t.ctypes.data
-        m.tex_w[i], m.tex_h[i], m.tex_c[i] = t.shape
-    return m, texptrs, tex_arrays
+    """the plain (unfolded, unhoisted) material program + host texture pointers, from the oracle's OWN
+    front-end (oracle/materials.py): a node graph (walked by duck typing), or an already built pod"""
+    from . import materials as M
+    if isinstance(material, tuple) and len(material) == 3 and isinstance(material[0], M.MaterialPOD):
+        return material
+    return M.material_pod_of(material)
+
+
+def _lighting_pod(lighting):
+    from . import materials as M
+    if isinstance(lighting, M.LightingPOD):
+        return lighting
+    if lighting is None:
+        return M.default_lighting()
+    return M.lighting_of(lighting)
 
 
 def pars_occup(verts, sizes, W2V, V2W, W, H, clipping=True, bias=(0.5, 0.5), depth=None):
@@ -107,7 +114,7 @@ def pars_occup(verts, sizes, W2V, V2W, W, H, clipping=True, bias=(0.5, 0.5), dep
 def pars_color(verts, sizes, colors, occup, W2V, V2W, W, H, material, lighting, image, bias=(0.5, 0.5)):
     """core/particle.py:129-161; shades pixels with occup != -1 into image (in place)."""
     m, texptrs, keep = _material_pod(material)
-    L = lighting.struct()
+    L = _lighting_pod(lighting)
     verts, sizes = _f(verts).reshape(-1, 3), _f(sizes).reshape(-1)
     colors = _f(colors).reshape(-1, 3) if colors is not None else None
     lib().orc_pars_color(_p(verts), _p(sizes), _p(colors), _p(np.ascontiguousarray(occup, dtype=np.int32)),
@@ -119,9 +126,10 @@ def pars_color(verts, sizes, colors, occup, W2V, V2W, W, H, material, lighting, 
 def render_color(verts, norms, coors, occup, W2V, V2W, W, H, flags, material, lighting, image, bias=(0.5, 0.5),
                  parallel=True):
     """Shades pixels with occup != -1 into `image` ([W,H,3] f32, modified in place and returned).
-    `material` is a taichi_three_b200 material node graph, `lighting` a taichi_three_b200.Lighting."""
+    `material`: a material node graph (the product's or the reference's classes, walked by oracle/materials.py) or a
+    pod built by oracle.materials.stock_*; `lighting`: a Lighting object, a LightingPOD, or None = the default light."""
     m, texptrs, tex_arrays = _material_pod(material)
-    L = lighting.struct()
+    L = _lighting_pod(lighting)
     verts = _f(verts).reshape(-1, 9)
     norms = _f(norms).reshape(-1, 9) if norms is not None else None
     coors = _f(coors).reshape(-1, 6) if coors is not None else None

@@ -894,6 +894,18 @@ void orc_transform_norms(float *v, int64_t n, const float *tn) {
     }
 }
 
+/* bench.py's reference arm: use `n` host threads whatever OMP_NUM_THREADS says (torchrun exports OMP_NUM_THREADS=1) */
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    extern void omp_set_num_threads(int);
+    extern void omp_set_dynamic(int);
+    omp_set_dynamic(0);
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int orc_num_threads(void) {
 #ifdef _OPENMP
     extern int omp_get_max_threads(void);

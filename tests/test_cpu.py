@@ -256,3 +256,68 @@ def test_three_address_prologue_equals_postfix(tina):
         for r, v in want.items():
             assert np.array_equal(got[r], v), (mat, r)
     assert forms[:4] == [1, 3, 4, 0]
+
+
+# ---- the oracle's own front-end (round 2) ---------------------------------------------------------------
+def test_oracle_workload_recipes_equal_the_bench_recipes(O, tina):
+    """oracle/workloads.py restates the camera and the C1 / C2 / C3 inputs without the product (bench.py --impl
+    reference); they must be the inputs the product-side bench renders."""
+    from oracle import workloads as R
+    for aspect in (1.0, 16 / 9):
+        v0, p0 = scenes.default_camera(aspect)
+        v1, p1 = R.default_camera(aspect)
+        assert np.array_equal(v0, v1) and np.array_equal(p0, p1)
+    assert np.array_equal(R.wave_grid_pos(48), scenes.wave_grid_pos(48))
+    assert np.array_equal(R.soup(5000, 320, 200, s=0.01, seed=7), scenes.soup(5000, 320, 200, s=0.01, seed=7))
+    v, _, _ = O.indexed(scenes.load_monkey())
+    assert np.array_equal(R.monkey_faces(os.path.join(ROOT, 'tests', 'assets', 'monkey.obj')), v)
+
+
+def test_oracle_material_front_end_is_independent_and_agrees(O, tina):
+    """oracle/materials.py flattens node graphs with its own walker (no product code): same programs as the product's
+    flattener on the stock materials and on composed graphs, and the node-free stock builders equal both."""
+    from oracle import materials as OM
+    from taichi_three_b200.material import flatten_material
+    src = open(os.path.join(ROOT, 'oracle', 'materials.py')).read() + open(os.path.join(ROOT, 'oracle', 'oracle.py')).read()
+    assert 'import taichi_three_b200' not in src and 'from taichi_three_b200' not in src
+    img = np.random.default_rng(0).random((4, 4, 3)).astype(np.float32)
+    graphs = [tina.Diffuse(), tina.Classic(), tina.PBR(), tina.Lamp(), tina.Diffuse(color=[.2, .4, .6]),
+              tina.PBR(basecolor=tina.Texture(img), metallic=0.3, roughness=0.2),
+              (tina.Classic(shineness=8) * 0.5 + tina.Lamp(color=[1, 0, 0])).mix(tina.PBR(metallic=1.0), tina.Texture(img))]
+
+    def code(m, n):
+        return [(m.code[i].op, m.code[i].arg, tuple(m.code[i].c)) for i in range(n)]
+    for g in graphs:
+        brdf, amb, emi, tex = flatten_material(g)
+        m, _, arrays = OM.material_pod_of(g)
+        assert (m.n_brdf, m.n_ambient, m.n_emission, m.ntex) == (len(brdf), len(amb), len(emi), len(tex))
+        want = [(op, arg, tuple(np.float32(x) for x in c)) for op, arg, c in brdf + amb + emi]
+        assert code(m, len(want)) == want
+    for pod, g in ((OM.stock_diffuse(), tina.Diffuse()), (OM.stock_classic(), tina.Classic())):
+        m, n = pod[0], pod[0].n_brdf + pod[0].n_ambient + pod[0].n_emission
+        assert code(m, n) == code(OM.material_pod_of(g)[0], n)
+    # lights: the default light of the parity tests
+    L = tina.Lighting()
+    L.add_light(dir=[1, 2, 3], color=[0.9, 0.9, 0.9])
+    L.set_ambient_light([0.1, 0.1, 0.1])
+    a, b = OM.lighting_of(L), OM.default_lighting()
+    assert bytes(a) == bytes(b) == bytes(L.struct())
+
+
+def test_bench_reference_arm_is_product_free_and_uses_every_core():
+    """`bench.py --impl reference` under torchrun's OMP_NUM_THREADS=1: every host core, the same config object as the
+    GPU arm, and no product module (nor libtina_b200.so) in the process."""
+    import json
+    import subprocess
+    import sys
+    env = dict(os.environ, OMP_NUM_THREADS='1')
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--workload', 'c1', '--steps', '1',
+                          '--warmup', '0'], capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line['impl'] == 'reference' and line['product_modules_loaded'] == []
+    assert line['cpu_baseline']['cores'] == len(os.sched_getaffinity(0))
+    sys.path.insert(0, ROOT)
+    import bench
+    assert line['config'] == bench.config_for('c1', 1)
+    assert line['e2e']['h2d_bytes_per_step'] == 0 and line['value'] > 0
