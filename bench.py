@@ -264,7 +264,7 @@ def make_env():
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
-    ncpus = bind_to_gpu_cpus(local_rank)
+    ncpus = None if os.environ.get('TINA_BENCH_NOBIND') else bind_to_gpu_cpus(local_rank)
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     if world > 1:
@@ -379,7 +379,8 @@ def c5_measure(env, K, warmup, nfaces=None):
     out = dict(ms_per_frame=ms, mtris_per_s=N / ms / 1e3, frames_per_s=1e3 / ms, faces=N,
                step_ms_min_median_max=[float(step_ms.min()), float(np.median(step_ms)), float(step_ms.max())],
                composite='keys MIN over peer key buffers inside k_render_color (NVLink loads), image strips stored to rank 0' if world > 1 else 'single GPU',
-               nvlink_bytes_per_frame=(W * H * 8 * (world - 1) // world + W * H * 12 * (world - 1) // world) * world if world > 1 else 0)
+               # every rank reads its strip of the other ranks' keys; every rank but the root stores its image strip to the root
+               nvlink_bytes_per_frame=(world - 1) * W * H * 8 + (world - 1) * W * H * 12 // world)
     # checksums that must not depend on the number of GPUs: the composited image (complete on rank 0) and, per strip
     # owner, the composited keys of its strip
     npix = W * H

@@ -1163,3 +1163,76 @@ def test_grid_tile_rasteriser_equals_gather_kernel(tina, O, n, W, H):
         assert np.array_equal(d.astype(np.int32), ref['depth'])
         assert np.array_equal(o.astype(np.int32), ref['occups'][-1])
         _check_frame(scene, ref)
+
+
+# ---- parity at BASELINE.json sizes (C2 is test_c2_full_size_bit_exact) ------------------------------------------
+def test_c2b_full_size_nocull_bit_exact(tina, O):
+    """C2b: the reference's own example wraps the grid in MeshNoCulling (examples/meshgrid_wave.py:21): 4,186,116 faces."""
+    n, W, H = 1024, 1920, 1080
+    pos = scenes.wave_grid_pos(n)
+    scene = tina.Scene((W, H), smoothing=True, maxfaces=2**22)
+    grid = tina.MeshGrid(n)
+    grid.pos.from_numpy(pos)
+    scene.add_object(tina.MeshNoCulling(grid), tina.Classic())
+    view, proj = scenes.default_camera(W / H)
+    scene.engine.set_camera(view, proj)
+    scene.render()
+    fv, fn, _ = O.no_culling(O.grid_faces(pos), O.grid_faces(O.grid_normals(pos)))
+    ref = O.render_scene([(fv, fn, None, tina.Classic())], W, H, view, proj, scene.lighting, _flags(O, smoothing=True))
+    _check_frame(scene, ref)
+
+
+def _soup_engine(tina, N, W, H, s, seed):
+    import torch
+    view, proj = scenes.default_camera(W / H)
+    tri = scenes.soup_torch(N, W, H, s, seed, torch.device('cuda', torch.cuda.current_device()))
+    engine = tina.Engine((W, H))
+    engine.set_camera(view, proj)
+    raster = tina.TriangleRaster(engine, maxfaces=N)
+    raster.set_face_verts(tri)
+    engine.clear_depth()
+    raster.render_occup()
+    torch.cuda.synchronize()
+    return engine, raster, tri, (proj @ view).astype(np.float32)
+
+
+def test_c3_full_size_ids_depth_bit_exact(tina, O):
+    """C3 at BASELINE size: 16,777,216-face soup at 3840x2160, depth complexity ~8 (atomic contention): face ids and
+    depth equal the serial oracle's on every pixel."""
+    from taichi_three_b200 import multigpu as M
+    W, H, N = 3840, 2160, 16 * 2**20
+    engine, raster, tri, W2V = _soup_engine(tina, N, W, H, scenes.SOUP_S_C3, 20240601)
+    occup, depth, tie, st = O.render_occup(tri.cpu().numpy(), W2V, W, H)
+    d, o = M.unpack_keys(engine.keys.cpu().view(W, H))
+    assert np.array_equal(d.numpy(), depth)
+    assert np.array_equal(o.numpy(), occup)
+    assert 7.0 < st['covered'] / (W * H) < 9.0  # the recipe's depth complexity
+
+
+def test_c5_prefix_at_8k_ids_depth_bit_exact(tina, O):
+    """C5: the 2^24-face prefix of the 134 M-face soup at 7680x4320 against the serial oracle."""
+    from taichi_three_b200 import multigpu as M
+    W, H, N = 7680, 4320, 2**24
+    engine, raster, tri, W2V = _soup_engine(tina, N, W, H, scenes.SOUP_S_C5, 20240602)
+    occup, depth, tie, st = O.render_occup(tri.cpu().numpy(), W2V, W, H)
+    d, o = M.unpack_keys(engine.keys.cpu().view(W, H))
+    assert np.array_equal(d.numpy(), depth)
+    assert np.array_equal(o.numpy(), occup)
+    assert (occup >= 0).mean() > 0.5
+
+
+def test_c4_full_resolution_views(tina, O):
+    """C4 at BASELINE resolution: cornell.gltf at 1024x1024, 8 of the 64 batch views (every eighth camera): ids + depth
+    bit-exact, colour within 1e-4 (PBR + 512^2 texture)."""
+    W = H = 1024
+    cams = scenes.cornell_views(64)
+    gltf = scenes.load_cornell()
+    scene = tina.Scene((W, H), smoothing=True, texturing=True)
+    gltf.extract(scene)
+    objs = scenes.cornell_oracle_objects(gltf)
+    for k in range(0, 64, 8):
+        view, proj = cams[k]
+        scene.engine.set_camera(view, proj)
+        scene.render()
+        ref = O.render_scene(objs, W, H, view, proj, scene.lighting, _flags(O, smoothing=True, texturing=True))
+        _check_frame(scene, ref)
