@@ -223,9 +223,14 @@ enum {
     TINA_SINK_CHESSBOARD = 7, /* shader.py:71-79  */
     TINA_SINK_VIEWDIR = 8,    /* shader.py:96-101 */
     TINA_SINK_SIMPLE = 9,     /* shader.py:104-109 */
+    TINA_SINK_ELMID = 10,     /* probe.py:21-22: the visible face's id (ProbeShader.elmid) */
 };
 int tina_raster_render_gbuffer(TinaRaster *r, int kind, void *out, int ncomp, int out_is_int, const float *param_host,
                                void *stream);
+/* the same for up to 8 sinks in ONE launch (a ShaderGroup's pre / post shaders, scene/raster.py:101-107): the face is
+ * gathered and the weights recomputed once per pixel.  Host arrays of nsinks entries; params_host: [nsinks][3] or NULL */
+int tina_raster_render_gbuffers(TinaRaster *r, int nsinks, const int *kinds_host, void *const *outs_host,
+                                const int *ncomps_host, const int *is_int_host, const float *params_host, void *stream);
 /* materialise TriangleRaster.occup as int32[W*H] (-1 = none) for the last render_occup */
 int tina_raster_occup(TinaRaster *r, int32_t *occup, void *stream);
 /* write the expanded [N,3,3] / [N,3,2] copies of the current object (the reference's raster.verts /

@@ -12,7 +12,7 @@ from .material import (Node, Const, Param, Input, Texture, FresnelFactor, IMater
 from .assimp import readobj, readgltf, objverts, objnorms, objcoors, objorient, objautoscale
 from .lighting import Lighting
 from .shader import (IShader, Shader, ShaderGroup, ConstShader, PositionShader, DepthShader, NormalShader,
-                     ViewNormalShader, TexcoordShader, ColorShader, ChessboardShader, ViewdirShader, SimpleShader)
+                     ViewNormalShader, TexcoordShader, ColorShader, ChessboardShader, ViewdirShader, SimpleShader, ProbeShader)
 from .mesh import (MAX, SimpleMesh, MeshModel, MeshGrid, MeshTransform, MeshFlipCulling, MeshNoCulling,
                    MeshFlipNormal, MeshFlatNormal, MeshSmoothNormal, MeshEditBase)
 from .engine import Engine

@@ -18,7 +18,8 @@ TINA_MAX_REGS = 8
 OP3 = 0x100  # three-address prologue form (include/tina_b200.h)
 TINA_VM_VALUES = 16
 (SINK_CONST, SINK_POSITION, SINK_DEPTH, SINK_NORMAL, SINK_VIEWNORMAL, SINK_TEXCOORD, SINK_COLOR, SINK_CHESSBOARD,
- SINK_VIEWDIR, SINK_SIMPLE) = range(10)
+ SINK_VIEWDIR, SINK_SIMPLE, SINK_ELMID) = range(11)
+TINA_MAX_SINKS = 8
 
 
 class TinaLighting(C.Structure):
@@ -82,6 +83,7 @@ SIGNATURES = {
     'tina_shared_open': (_i, [_i, _vp, C.POINTER(_vp)]),
     'tina_shared_close': (_i, [_i, _vp]),
     'tina_raster_render_gbuffer': (_i, [_vp, _i, _vp, _i, _i, _fp, _vp]),
+    'tina_raster_render_gbuffers': (_i, [_vp, _i, C.POINTER(_i), C.POINTER(_vp), C.POINTER(_i), C.POINTER(_i), _fp, _vp]),
     'tina_raster_occup': (_i, [_vp, _vp, _vp]),
     'tina_raster_buffers': (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i64)]),
     'tina_raster_set_tuning': (_i, [_vp, _i, _i]),

@@ -662,13 +662,20 @@ k_render_color(const long long *__restrict__ keys, const float *__restrict__ ver
     __stcs(out, c.x), __stcs(out + 1, c.y), __stcs(out + 2, c.z);
 }
 
-// G-buffer sinks (core/shader.py:21-109): one attribute of the visible surface per pixel
+// G-buffer sinks (core/shader.py:21-109, probe.py:21-23): attributes of the visible surface per pixel.  One launch
+// serves every sink of a ShaderGroup (scene/raster.py:101-107): the face is gathered and the weights recomputed once.
+#define TINA_MAX_SINKS 8
+struct SinkTab {
+    int n;
+    int kind[TINA_MAX_SINKS], ncomp[TINA_MAX_SINKS], is_int[TINA_MAX_SINKS];
+    void *out[TINA_MAX_SINKS];
+    float p[TINA_MAX_SINKS][3];
+};
 template <bool IDX>
 __global__ void __launch_bounds__(256)
 k_gbuffer(const long long *__restrict__ keys, const float *__restrict__ verts, const float *__restrict__ norms,
           const float *__restrict__ coors, const __grid_constant__ Cam cam, uint32_t flags, unsigned base, unsigned nfaces,
-          int kind, void *__restrict__ outp, int ncomp, int out_is_int, float p0, float p1, float p2,
-          const __grid_constant__ Src S) {
+          const __grid_constant__ SinkTab T, const __grid_constant__ Src S) {
     pdl_wait();
     const int P = blockIdx.x * blockDim.x + threadIdx.x;
     if (P >= cam.W * cam.H) return;
@@ -676,18 +683,36 @@ k_gbuffer(const long long *__restrict__ keys, const float *__restrict__ verts, c
     const unsigned id = (unsigned)(unsigned long long)key;
     const unsigned f = id - 1u - base;
     if (id == 0u || f >= nfaces) return; // triangle.py:137-138: sinks are only written where this object is visible
-    float v[3] = {0.f, 0.f, 0.f};
-    if (kind == TINA_SINK_CONST) {
-        v[0] = p0, v[1] = p1, v[2] = p2;
-    } else if (kind == TINA_SINK_DEPTH) {
-        v[0] = v[1] = v[2] = (float)(int)(key >> 32); // shader.py:39-42: engine.depth[P]
-    } else if (kind == TINA_SINK_COLOR) {
-        v[0] = v[1] = v[2] = 1.0f; // triangle.py:48
-    } else {
-        ShadeIn in;
-        float px, py;
-        pixel_inputs<IDX>(P, f, verts, norms, coors, cam, flags, S, in, px, py);
-        if (kind == TINA_SINK_POSITION) {
+    bool need_inputs = false, need_view = false;
+    for (int k = 0; k < T.n; k++) {
+        const int kd = T.kind[k];
+        need_inputs |= kd == TINA_SINK_POSITION || kd == TINA_SINK_NORMAL || kd == TINA_SINK_VIEWNORMAL || kd == TINA_SINK_TEXCOORD ||
+                       kd == TINA_SINK_CHESSBOARD || kd == TINA_SINK_VIEWDIR || kd == TINA_SINK_SIMPLE;
+        need_view |= kd == TINA_SINK_VIEWDIR || kd == TINA_SINK_SIMPLE;
+    }
+    ShadeIn in;
+    float px = 0.f, py = 0.f;
+    V3 vd = v3(0.f, 0.f, 0.f);
+    if (need_inputs) pixel_inputs<IDX>(P, f, verts, norms, coors, cam, flags, S, in, px, py);
+    if (need_view) vd = view_direction(cam, px, py);
+    for (int k = 0; k < T.n; k++) {
+        const int kind = T.kind[k], ncomp = T.ncomp[k];
+        const float p0 = T.p[k][0], p1 = T.p[k][1], p2 = T.p[k][2];
+        float v[3] = {0.f, 0.f, 0.f};
+        if (kind == TINA_SINK_ELMID) { // probe.py:22: the face id itself (exact as an integer)
+            if (T.is_int[k]) {
+                int *o = reinterpret_cast<int *>(T.out[k]) + (long long)P * ncomp;
+                for (int c = 0; c < ncomp; c++) o[c] = (int)f;
+                continue;
+            }
+            v[0] = v[1] = v[2] = (float)f;
+        } else if (kind == TINA_SINK_CONST) {
+            v[0] = p0, v[1] = p1, v[2] = p2;
+        } else if (kind == TINA_SINK_DEPTH) {
+            v[0] = v[1] = v[2] = (float)(int)(key >> 32); // shader.py:39-42: engine.depth[P]
+        } else if (kind == TINA_SINK_COLOR) {
+            v[0] = v[1] = v[2] = 1.0f; // triangle.py:48
+        } else if (kind == TINA_SINK_POSITION) {
             v[0] = in.pos.x, v[1] = in.pos.y, v[2] = in.pos.z;
         } else if (kind == TINA_SINK_NORMAL) {
             v[0] = in.normal.x, v[1] = in.normal.y, v[2] = in.normal.z;
@@ -702,20 +727,17 @@ k_gbuffer(const long long *__restrict__ keys, const float *__restrict__ verts, c
             const float fac = fmodf(floorf(px / p0) + floorf(py / p0), 2.0f);
             const float m = fac < 0.0f ? fac + 2.0f : fac; // python-style modulo
             v[0] = v[1] = v[2] = 0.4f * (1.0f - m) + 0.9f * m;
-        } else {
-            const V3 vd = view_direction(cam, px, py);
-            if (kind == TINA_SINK_VIEWDIR) { // shader.py:96-101
-                v[0] = vd.x * 0.5f + 0.5f, v[1] = vd.y * 0.5f + 0.5f, v[2] = vd.z * 0.5f + 0.5f;
-            } else { // TINA_SINK_SIMPLE, shader.py:104-109
-                v[0] = v[1] = v[2] = fabsf(dot3(in.normal, vd));
-            }
+        } else if (kind == TINA_SINK_VIEWDIR) { // shader.py:96-101
+            v[0] = vd.x * 0.5f + 0.5f, v[1] = vd.y * 0.5f + 0.5f, v[2] = vd.z * 0.5f + 0.5f;
+        } else { // TINA_SINK_SIMPLE, shader.py:104-109
+            v[0] = v[1] = v[2] = fabsf(dot3(in.normal, vd));
         }
-    }
-    if (out_is_int) {
-        int *o = reinterpret_cast<int *>(outp) + (long long)P * ncomp;
-        for (int k = 0; k < ncomp; k++) o[k] = (int)v[k];
-    } else {
-        float *o = reinterpret_cast<float *>(outp) + (long long)P * ncomp;
-        for (int k = 0; k < ncomp; k++) o[k] = v[k];
+        if (T.is_int[k]) {
+            int *o = reinterpret_cast<int *>(T.out[k]) + (long long)P * ncomp;
+            for (int c = 0; c < ncomp; c++) o[c] = (int)v[c];
+        } else {
+            float *o = reinterpret_cast<float *>(T.out[k]) + (long long)P * ncomp;
+            for (int c = 0; c < ncomp; c++) o[c] = v[c];
+        }
     }
 }

@@ -113,16 +113,31 @@ class MeshModel:
         faces = np.asarray(obj['f'])
         if faces.ndim == 2:  # model.py:23-24: same index for v / vt / vn
             faces = np.stack([faces, faces, faces], axis=2)
-        self.faces = torch.as_tensor(np.ascontiguousarray(faces.astype(np.uint32).astype(np.int64).astype(np.int32))).to(dev)
         v = np.asarray(obj['v'], dtype=np.float32)
         vt = np.asarray(obj.get('vt', np.zeros((1, 2))), dtype=np.float32)[:, :2]
         vn = np.asarray(obj.get('vn', np.zeros((1, 3))), dtype=np.float32)
+        # The kernels index `faces` as int32 [N, 3 corners, 3 = v / vt / vn] without bounds checks: validate here.
+        # (The reference fails in from_numpy on a shape mismatch, model.py:25-31; readobj yields [N,3,1] for `f 1 2 3`
+        # and [N,3,2] for `f 1/1 2/2`: missing vt / vn columns are filled with index 0 like obj.py:73 does.)
+        if faces.ndim != 3 or faces.shape[1] != 3 or not 1 <= faces.shape[2] <= 3:
+            raise ValueError(f"MeshModel: 'f' must be [N,3] or [N,3,k<=3] vertex / texcoord / normal indices, got shape {faces.shape}")
+        if faces.shape[2] < 3:
+            faces = np.concatenate([faces, np.zeros(faces.shape[:2] + (3 - faces.shape[2],), faces.dtype)], axis=2)
+        faces = faces.astype(np.int64)
+        for col, name in ((1, 'vt'), (2, 'vn')):  # attribute absent from the dict: one placeholder element, index 0
+            if name not in obj:
+                faces[:, :, col] = 0
+        for col, (name, arr) in enumerate((('v', v), ('vt', vt), ('vn', vn))):
+            if len(faces) and (faces[:, :, col].min() < 0 or faces[:, :, col].max() >= max(len(arr), 1)):
+                raise ValueError(f"MeshModel: '{name}' index out of range [0, {len(arr)}) in 'f' "
+                                 f'(min {faces[:, :, col].min()}, max {faces[:, :, col].max()}; relative OBJ indices are not supported)')
+        self.faces = torch.as_tensor(np.ascontiguousarray(faces.astype(np.int32))).to(dev)
         self.verts = torch.as_tensor(np.ascontiguousarray(v)).to(dev)
         self.coors = torch.as_tensor(np.ascontiguousarray(vt)).to(dev)
         self.norms = torch.as_tensor(np.ascontiguousarray(vn)).to(dev)
         self.maxfaces, self.maxverts = len(faces), len(v)
         self.maxcoors, self.maxnorms = len(vt), len(vn)
-        self._host = {'f': faces.astype(np.int64), 'v': v}
+        self._host = {'f': faces, 'v': v}
 
     def get_npolygon(self):
         return 3
@@ -259,14 +274,23 @@ class MeshFlatNormal(MeshEditBase):
         s = self.mesh._source()
         if s.kind != 'indexed':
             raise NotImplementedError('MeshFlatNormal needs an indexed mesh')
-        host = self.mesh._host
+        host = _model_host(self.mesh, 'MeshFlatNormal')
         fv = host['f'][:, :, 0]
-        nrm = _face_normals(host['v'], fv)
+        nrm = _face_normals(host['v'], fv)  # (from the mesh's CURRENT vertices: norm.py:5-14 computes per frame)
         faces = host['f'].copy()
         faces[:, :, 2] = np.arange(len(faces))[:, None]
         s.vn = torch.as_tensor(np.ascontiguousarray(nrm)).to(s.v.device)
         s.faces = torch.as_tensor(np.ascontiguousarray(faces.astype(np.int32))).to(s.v.device)
         return s
+
+
+def _model_host(mesh, who):
+    """Index buffer + the CURRENT vertex positions of a MeshModel as numpy (the normal adapters recompute from what
+    mesh.verts holds now, like the reference's pre_compute, mesh/norm.py:28-55).  Wrapped meshes are not supported:
+    their transform / flip would have to be applied before the normals are computed."""
+    if not isinstance(mesh, MeshModel):
+        raise NotImplementedError(f'{who} takes a MeshModel (got {type(mesh).__name__}); apply MeshTransform / culling wrappers outside it')
+    return {'f': mesh._host['f'], 'v': mesh.verts.detach().cpu().numpy()}
 
 
 class MeshSmoothNormal(MeshEditBase):
@@ -279,7 +303,7 @@ class MeshSmoothNormal(MeshEditBase):
         self._norm = None
 
     def update_normal(self):
-        host = self.mesh._host
+        host = _model_host(self.mesh, 'MeshSmoothNormal')
         fv = host['f'][:, :, 0]
         fn = _face_normals(host['v'], fv)
         acc = np.zeros((len(host['v']), 3), dtype=np.float32)

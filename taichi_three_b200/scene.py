@@ -140,12 +140,16 @@ class Scene:
         bg = np.broadcast_to(np.asarray(self.bgcolor, dtype=np.float32), (3,))
         if not items:
             self.image.fill(bg)
-        fuse_tm = bool(self.tonemap) and len(items) == 1 and not self.blooming and not self.ssao
+        def fuses(raster):  # rasterisers whose render_color takes the fill / tonemap fusion hints
+            return isinstance(raster, TriangleRaster) or hasattr(raster, 'set_particles')
+        # the ACES curve rides along only when the frame's single object is shaded by a pass that applies it
+        # (a wireframe-only scene is tonemapped by the separate pass below, like every multi-object frame)
+        fuse_tm = bool(self.tonemap) and len(items) == 1 and not self.blooming and not self.ssao and fuses(items[0][1].raster)
         for i, (obj, info) in enumerate(items):
             shader = self.shaders[id(info.material)]
             info.raster.set_object(obj)
             info.raster.render_occup()
-            if isinstance(info.raster, TriangleRaster) or hasattr(info.raster, 'set_particles'):
+            if fuses(info.raster):
                 info.raster.render_color(shader, fill_bg=bg if i == 0 else None, tonemap=fuse_tm)
             else:
                 if i == 0:

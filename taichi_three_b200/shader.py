@@ -76,6 +76,53 @@ class SimpleShader(_Sink):  # shader.py:104-109
     kind = 9
 
 
+class _ElmidSink(_Sink):  # probe.py:21-22
+    kind = 10
+
+
+class ProbeShader:
+    """tina/probe.py:5-29: per-pixel id of the visible face (`elmid`, -1 = none) and its interpolated texture
+    coordinate (`texcoord`), for picking / painting (`scene.post_shaders.append(probe)` before the objects are added).
+    Face ids are those of the object rendered last at that pixel, like the reference's (its `f`)."""
+
+    def __init__(self, res):
+        import torch
+        from .field import Field
+        res = (res, res) if isinstance(res, int) else tuple(res)
+        self.res = (int(res[0]), int(res[1]))
+        dev = torch.device('cuda', torch.cuda.current_device())
+        self.elmid = Field(torch.full(self.res, -1, dtype=torch.int32, device=dev))
+        self.texcoord = Field(torch.zeros(self.res + (2,), dtype=torch.float32, device=dev))
+        self._parts = (_ElmidSink(self.elmid), TexcoordShader(self.texcoord))
+
+    def clear_buffer(self):  # probe.py:11-15
+        self.elmid.fill(-1)
+        self.texcoord.fill(0)
+
+    def _sinks(self):
+        return self._parts
+
+    def touch(self, callback, mx, my, rad):
+        """probe.py:25-35: call `callback(probe, (x, y), r)` for every pixel within `rad` of the cursor (mx, my in
+        [0, 1]) that shows a face.  The reference's callback is a Taichi function; here it is a Python callable run
+        on the host over the (small) disc."""
+        import numpy as np
+        p = np.float32([mx, my]) * np.float32(self.res)
+        bot = np.floor(p - np.float32(rad)).astype(int)
+        top = np.ceil(p + np.float32(rad)).astype(int)
+        x0, y0 = max(int(bot[0]), 0), max(int(bot[1]), 0)
+        x1, y1 = min(int(top[0]), self.res[0] - 1), min(int(top[1]), self.res[1] - 1)
+        if x1 < x0 or y1 < y0:
+            return
+        ids = self.elmid.to_torch()[x0:x1 + 1, y0:y1 + 1].cpu().numpy()
+        for x in range(x0, x1 + 1):
+            for y in range(y0, y1 + 1):
+                r = float(np.sqrt(np.float32((x - p[0]) ** 2 + (y - p[1]) ** 2)))
+                if r > rad or ids[x - x0, y - y0] == -1:
+                    continue
+                callback(self, (x, y), r)
+
+
 class Shader(IShader):
     def __init__(self, img, lighting, material):
         super().__init__(img)

@@ -146,12 +146,15 @@ class TriangleRaster:
                 self._bg_cache = (fill_bg, bg)
             bg = bg[1]
         st = _stream(self._dev_index)
+        # every G-buffer sink of the group (pre / post shaders, ProbeShader parts) goes into ONE launch
+        sinks = [p for s in shaders for p in (s._sinks() if hasattr(s, '_sinks') else ((s,) if isinstance(s, _Sink) else ()))]
+        for i in range(0, len(sinks), _lib.TINA_MAX_SINKS):
+            self._render_sinks(sinks[i:i + _lib.TINA_MAX_SINKS], st)
         for s in shaders:
+            if isinstance(s, _Sink) or hasattr(s, '_sinks'):
+                continue
             rec = self._shader_cache.get(id(s))
             img = s.img
-            if isinstance(s, _Sink):
-                self._render_sink(s, st)
-                continue
             if rec is None or rec[0] is not s or rec[1] is not img:
                 if not isinstance(s, Shader):
                     raise NotImplementedError(f'{type(s).__name__} is not supported by the B200 render_color yet')
@@ -195,18 +198,23 @@ class TriangleRaster:
                                                                  _stream(self._dev_index)))
         self._mat_keep = keep
 
-    def _render_sink(self, s, st):
-        """G-buffer shaders (shader.py:21-109) for the current object."""
-        t = s.img.to_torch() if hasattr(s.img, 'to_torch') else s.img
+    def _render_sinks(self, sinks, st):
+        """G-buffer shaders (shader.py:21-109, probe.py:21-23) for the current object: one launch for all of them."""
+        n = len(sinks)
         npix = self.res[0] * self.res[1]
-        if t.dtype not in (torch.float32, torch.int32) or not t.is_contiguous() or not t.is_cuda or t.numel() % npix:
-            raise ValueError('G-buffer image must be a contiguous float32 / int32 CUDA tensor [W, H] or [W, H, n]')
-        ncomp = t.numel() // npix
-        if not 1 <= ncomp <= 3:
-            raise ValueError('G-buffer image must have 1..3 components')
-        p = s.param()
-        _lib.check(_lib.lib().tina_raster_render_gbuffer(self._h, s.kind, C.c_void_p(t.data_ptr()), ncomp,
-                                                         1 if t.dtype == torch.int32 else 0, _fp(p) if p is not None else None, st))
+        kinds, outs, ncomps, isint = (C.c_int * n)(), (C.c_void_p * n)(), (C.c_int * n)(), (C.c_int * n)()
+        params = np.zeros((n, 3), dtype=np.float32)
+        for i, s in enumerate(sinks):
+            t = s.img.to_torch() if hasattr(s.img, 'to_torch') else s.img
+            if t.dtype not in (torch.float32, torch.int32) or not t.is_contiguous() or not t.is_cuda or t.numel() % npix:
+                raise ValueError('G-buffer image must be a contiguous float32 / int32 CUDA tensor [W, H] or [W, H, n]')
+            if not 1 <= t.numel() // npix <= 3:
+                raise ValueError('G-buffer image must have 1..3 components')
+            kinds[i], outs[i], ncomps[i], isint[i] = s.kind, t.data_ptr(), t.numel() // npix, 1 if t.dtype == torch.int32 else 0
+            p = s.param()
+            if p is not None:
+                params[i] = np.asarray(p, dtype=np.float32).reshape(-1)[:3]
+        _lib.check(_lib.lib().tina_raster_render_gbuffers(self._h, n, kinds, outs, ncomps, isint, _fp(params), st))
 
     def _material_struct(self, material):
         """Flattening + folding is pure host work: cache it per material object, keyed by the

@@ -1236,3 +1236,117 @@ def test_c4_full_resolution_views(tina, O):
         scene.render()
         ref = O.render_scene(objs, W, H, view, proj, scene.lighting, _flags(O, smoothing=True, texturing=True))
         _check_frame(scene, ref)
+
+
+def test_probe_shader_and_fused_sinks(tina, O):
+    """tina/probe.py: ProbeShader as a post-shader records the visible face id and its texture coordinate per pixel
+    (elmid == raster.occup, texcoord == the TexcoordShader sink == the oracle's G-buffer); `touch` visits the disc
+    around the cursor.  All sinks of the group travel in one launch (tina_raster_render_gbuffers): more than eight
+    sinks split into two launches with the same results."""
+    import torch
+    from taichi_three_b200 import _lib
+    W, H = 200, 160
+    obj = scenes.load_monkey()
+    scene = tina.Scene((W, H), smoothing=True, texturing=True)
+    probe = tina.ProbeShader(scene.res)
+    tc = torch.zeros((W, H, 2), device='cuda')
+    extra = [torch.zeros((W, H, 3), device='cuda') for _ in range(7)]
+    scene.post_shaders.append(probe)
+    scene.post_shaders.append(tina.TexcoordShader(tina.Field(tc)))
+    for b in extra:  # 2 + 2 + 7 = 11 sink parts: two launches
+        scene.post_shaders.append(tina.NormalShader(tina.Field(b)))
+    scene.add_object(tina.MeshModel(obj), tina.Classic())
+    view, proj = scenes.default_camera(W / H)
+    scene.engine.set_camera(view, proj)
+    l0 = _lib.lib().tina_launch_count()
+    scene.render()
+    torch.cuda.synchronize()
+    occup = scene.triangle_raster.occup.to_numpy()
+    assert np.array_equal(probe.elmid.to_numpy(), occup) and (occup >= 0).sum() > 3000
+    assert np.array_equal(probe.texcoord.to_numpy(), tc.cpu().numpy())
+    for b in extra[1:]:
+        assert torch.equal(b, extra[0])
+    v, vn, vt = O.indexed(obj)
+    W2V = (proj @ view).astype(np.float32)
+    V2W = np.linalg.inv(proj @ view).astype(np.float32)
+    flags = _flags(O, smoothing=True, texturing=True)
+    o_occ, o_dep, _, _ = O.render_occup(v, W2V, W, H, flags)
+    ref = O.render_gbuffer(5, v, vn, vt, o_occ, o_dep, W2V, V2W, W, H, flags, np.zeros((W, H, 2), np.float32))
+    assert np.array_equal(o_occ, occup)
+    assert np.abs(probe.texcoord.to_numpy() - ref).max() <= 1e-6
+    # touch: every covered pixel within the radius, with its distance
+    hits = []
+    probe.touch(lambda p, I, r: hits.append((I, r)), 0.5, 0.5, 6.0)
+    cx, cy = 0.5 * W, 0.5 * H
+    want = {(x, y) for x in range(W) for y in range(H) if np.hypot(x - cx, y - cy) <= 6.0 and occup[x, y] != -1}
+    assert {I for I, _ in hits} == want and len(want) > 50
+    # the second frame clears the probe first (clear_buffer): an empty scene leaves elmid == -1
+    scene2 = tina.Scene((W, H))
+    probe2 = tina.ProbeShader(scene2.res)
+    scene2.post_shaders.append(probe2)
+    probe2.elmid.fill(5)
+    scene2.render()
+    assert (probe2.elmid.to_numpy() == -1).all()
+
+
+def test_wireframe_only_scene_is_tonemapped(tina, O):
+    """a scene whose single object goes through a raster without fused tonemap (wireframe) must still get the
+    ACES pass (scene/raster.py:202-203 applies it unconditionally)."""
+    import torch
+    W, H = 96, 64
+    view, proj = scenes.default_camera(W / H)
+    tri = np.float32([[[-1, -1, 0], [1, -1, 0], [0, 1, 0]]])
+
+    def frame(tonemap):
+        scene = tina.Scene((W, H), tonemap=tonemap, linecolor=[2.0, 1.5, 0.5])
+        mesh = tina.SimpleMesh()
+        mesh.set_face_verts(tri)
+        scene.add_object(tina.MeshToWire(mesh))
+        scene.engine.set_camera(view, proj)
+        scene.render()
+        torch.cuda.synchronize()
+        return scene.img.to_numpy()
+    lin, tm = frame(False), frame(True)
+    assert lin.max() > 1.0
+    assert np.abs(tm - O.tonemap(lin)).max() <= 1e-6 and np.abs(tm - lin).max() > 0.1
+
+
+def test_meshmodel_validates_indices_and_normal_adapters_follow_vertices(tina, O):
+    """MeshModel rejects index buffers the kernels would read out of bounds with; [N,3,1] / [N,3,2] OBJ index
+    layouts are padded like assimp/obj.py:73; MeshSmoothNormal / MeshFlatNormal recompute from the mesh's current vertices
+    (mesh/norm.py:5-55)."""
+    import torch
+    obj = scenes.load_monkey()
+    with pytest.raises(ValueError):
+        tina.MeshModel({'v': obj['v'], 'f': np.asarray(obj['f'])[:, :, :1] + len(obj['v'])})
+    with pytest.raises(ValueError):
+        tina.MeshModel({'v': obj['v'], 'f': -np.ones((4, 3), int)})
+    with pytest.raises(ValueError):
+        tina.MeshModel({'v': obj['v'], 'f': np.zeros((4, 4, 3), int)})
+    m1 = tina.MeshModel({'v': obj['v'], 'f': np.asarray(obj['f'])[:, :, :1]})  # `f 1 2 3` layout
+    assert tuple(m1.faces.shape[1:]) == (3, 3) and int(m1.faces[:, :, 1:].abs().max()) == 0
+    # smooth normals follow an edit of mesh.verts
+    W, H = 160, 120
+    view, proj = scenes.default_camera(W / H)
+    model = tina.MeshModel(obj)
+    sm = tina.MeshSmoothNormal(model, cached=False)
+    scene = tina.Scene((W, H), smoothing=True, tonemap=False)
+    scene.add_object(sm, tina.Classic())
+    scene.engine.set_camera(view, proj)
+    scene.render()
+    a = scene.img.to_numpy().copy()
+    model.verts[:, 2] *= 0.3  # flatten the head: different normals, different shading
+    scene.render()
+    torch.cuda.synchronize()
+    b = scene.img.to_numpy()
+    v = model.verts.cpu().numpy()
+    f = np.asarray(obj['f'])[:, :, 0]
+    fn = np.cross(v[f[:, 1]] - v[f[:, 0]], v[f[:, 2]] - v[f[:, 0]]).astype(np.float32)
+    fn = (fn * (np.float32(1) / np.sqrt((fn * fn).sum(1, keepdims=True)))).astype(np.float32)
+    acc = np.zeros_like(v)
+    for k in range(3):
+        np.add.at(acc, f[:, k], fn)
+    vn = (acc * (np.float32(1) / np.sqrt((acc * acc).sum(1, keepdims=True)))).astype(np.float32)
+    ref = O.render_scene([(v[f], vn[f], None, tina.Classic())], W, H, view, proj, scene.lighting, _flags(O, smoothing=True), do_tonemap=False)
+    assert np.abs(b - ref['image']).max() <= 5e-4  # (summation order of the per-vertex accumulation differs)
+    assert np.abs(a - b).max() > 0.05
