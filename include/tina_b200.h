@@ -236,6 +236,10 @@ int tina_raster_occup(TinaRaster *r, int32_t *occup, void *stream);
 /* write the expanded [N,3,3] / [N,3,2] copies of the current object (the reference's raster.verts /
  * norms / coors fields, triangle.py:18-22) if the indexed path skipped them */
 int tina_raster_materialize(TinaRaster *r, void *stream);
+/* the reference's public per-face setup cache (triangle.py:25-29,127-131) of the current object under the current camera,
+ * materialised on demand: bcn, can, boo, coo [nfaces][2], wsc [nfaces][3] (device); only faces that pass cull + clip are
+ * written, like the reference */
+int tina_raster_setup_cache(TinaRaster *r, float *bcn, float *can, float *boo, float *coo, float *wsc, void *stream);
 /* device views of the current object's expanded attribute buffers (NULL until materialised) */
 int tina_raster_buffers(TinaRaster *r, const float **verts, const float **norms, const float **coors,
                         int64_t *nfaces);

@@ -85,6 +85,7 @@ SIGNATURES = {
     'tina_raster_render_gbuffer': (_i, [_vp, _i, _vp, _i, _i, _fp, _vp]),
     'tina_raster_render_gbuffers': (_i, [_vp, _i, C.POINTER(_i), C.POINTER(_vp), C.POINTER(_i), C.POINTER(_i), _fp, _vp]),
     'tina_raster_occup': (_i, [_vp, _vp, _vp]),
+    'tina_raster_setup_cache': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'tina_raster_buffers': (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i64)]),
     'tina_raster_set_tuning': (_i, [_vp, _i, _i]),
     'tina_raster_stats': (_i, [_vp, C.POINTER(_i64)]),

@@ -242,6 +242,27 @@ class TriangleRaster:
             self._occup_stale = False
         return Field(self._occup)
 
+    def _setup_cache(self, which):
+        """triangle.py:25-29: bcn / can / boo / coo [maxfaces, 2], wsc [maxfaces, 3] -- the per-face setup the reference
+        stores during render_occup (:127-131, faces that pass cull + clip only; other rows keep earlier contents).  The
+        kernels here recompute it on the fly, so the fields are filled on demand for the current object and camera."""
+        c = self.__dict__.get('_cache_fields')
+        if c is None:
+            dev = self.engine.device
+            c = {k: torch.zeros((self.maxfaces, 3 if k == 'wsc' else 2), dtype=torch.float32, device=dev)
+                 for k in ('bcn', 'can', 'boo', 'coo', 'wsc')}
+            self._cache_fields = c
+        if self.nfaces:
+            _lib.check(_lib.lib().tina_raster_setup_cache(self._h, *(C.c_void_p(c[k].data_ptr()) for k in ('bcn', 'can', 'boo', 'coo', 'wsc')),
+                                                          _stream()))
+        return Field(c[which])
+
+    bcn = property(lambda self: self._setup_cache('bcn'))
+    can = property(lambda self: self._setup_cache('can'))
+    boo = property(lambda self: self._setup_cache('boo'))
+    coo = property(lambda self: self._setup_cache('coo'))
+    wsc = property(lambda self: self._setup_cache('wsc'))
+
     def _buffers(self):
         # the indexed path (MeshGrid / MeshModel) keeps no expanded copies until somebody reads them
         _lib.check(_lib.lib().tina_raster_materialize(self._h, _stream()))

@@ -383,6 +383,96 @@ def case_micro():
         render_and_dump(f'micro_adversarial_cull{int(culling)}', scene, ['Diffuse()'])
 
 
+def case_setup_cache():
+    """The public per-face setup cache of the reference's TriangleRaster (triangle.py:25-29, written at :127-131):
+    bcn / can / boo / coo / wsc after render_occup, culling + clipping on (rows of rejected faces stay zero)."""
+    scene = tina.Scene((72, 64))
+    scene.add_object(tina.MeshModel(os.path.join(REF, 'assets/monkey.obj')))
+    camera(scene, 72 / 64, back=(0.6, 0.2, 2.7))
+    render_and_dump('setup_cache_monkey', scene, ['Diffuse()'])
+    r = scene.triangle_raster
+    n = int(r.nfaces[None])
+    path = os.path.join(HERE, 'setup_cache_monkey.npz')
+    d = dict(np.load(path))
+    for k in ('bcn', 'can', 'boo', 'coo', 'wsc'):
+        d[k] = getattr(r, k).to_numpy()[:n].astype(np.float32)
+    np.savez_compressed(path, **d)
+
+
+def random_material_spec(rng, depth=0):
+    """A random material graph as an expression over the node classes both code bases share."""
+    def color():
+        c = rng.integers(0, 4)
+        if c == 0:
+            return 'Texture(tex0)'
+        if c == 1:
+            return "'color'"
+        return repr([round(float(x), 3) for x in rng.uniform(0.05, 1.0, 3)])
+
+    def factor():
+        c = rng.integers(0, 5)
+        if c == 0:
+            return 'Texture(tex1)'
+        if c == 1:
+            return f'FresnelFactor(metallic={round(float(rng.uniform(0, 1)), 3)}, albedo={color()}, specular={round(float(rng.uniform(0.2, 0.8)), 3)})'
+        return repr(round(float(rng.uniform(0.05, 0.95)), 3))
+    leafs = ['Lambert()', 'Emission()',
+             lambda: f'Phong(shineness={int(rng.integers(2, 48))})',
+             lambda: f'CookTorrance(roughness={round(float(rng.uniform(0.25, 0.9)), 3)}, fresnel={factor()})',
+             lambda: f'Diffuse(color={color()})',
+             lambda: f'Classic(color={color()}, shineness={int(rng.integers(2, 48))}, specular={round(float(rng.uniform(0.1, 0.7)), 3)})',
+             lambda: f'PBR(basecolor={color()}, metallic={round(float(rng.uniform(0, 1)), 3)}, roughness={round(float(rng.uniform(0.3, 0.9)), 3)})',
+             lambda: f'Lamp(color={color()})']
+    if depth >= 2 or rng.random() < 0.25:
+        leaf = leafs[rng.integers(0, len(leafs))]
+        return leaf if isinstance(leaf, str) else leaf()
+    c = rng.integers(0, 3)
+    a, b = random_material_spec(rng, depth + 1), random_material_spec(rng, depth + 1)
+    if c == 0:
+        return f'MixMaterial({a}, {b}, {factor()})'
+    if c == 1:
+        return f'ScaleMaterial({a}, {color() if rng.random() < 0.5 else factor()})'
+    return f'AddMaterial({a}, {b})'
+
+
+def case_matgraphs():
+    """36 random material graphs (Mix / Scale / Add over Lambert, Phong, CookTorrance, Emission, the Diffuse / Classic /
+    PBR / Lamp constructors, colour and scalar textures, Fresnel factors as mix factors) shaded by the reference's own
+    matr/material.py + matr/nodes.py + core/lighting.py on one small smooth, textured object under a directional and a
+    point light.  Pins the oracle's independent material front-end (oracle/materials.py) and, through it, the CUDA path."""
+    rng = np.random.default_rng(20241017)
+    tex0 = rng.random((6, 5, 3)).astype(np.float32)
+    tex1 = rng.random((4, 7)).astype(np.float32)[:, :, None] * np.ones((1, 1, 3), np.float32)  # a scalar texture, as RGB
+    ns = {n: getattr(tina, n) for n in ('PBR', 'Classic', 'Diffuse', 'Lamp', 'Lambert', 'Phong', 'Emission', 'CookTorrance', 'Texture',
+                                        'FresnelFactor', 'MixMaterial', 'ScaleMaterial', 'AddMaterial')}
+    ns.update(tex0=tex0, tex1=tex1)
+    specs = [random_material_spec(rng) for _ in range(36)]
+    out = None
+    for i, spec in enumerate(specs):
+        scene = tina.Scene((36, 30), smoothing=True, texturing=True, tonemap=False)
+        mesh = tina.MeshGrid(9)
+        pos = mesh.pos.to_numpy()
+        xy = pos[..., :2].astype(np.float64)
+        pos[..., 2] = (0.25 * np.sin(4 * xy[..., 0]) * np.cos(3 * xy[..., 1])).astype(np.float32)
+        mesh.pos.from_numpy(pos)
+        scene.add_object(mesh, eval(spec, dict(ns)))
+        scene.lighting.add_light(pos=[0.4, 0.6, 1.5], color=[0.5, 0.7, 0.9])
+        camera(scene, 36 / 30, back=(0.4, 0.7, 2.2))
+        render_and_dump('matgraphs_tmp', scene, [spec], textures=[tex0, tex1])
+        d = dict(np.load(os.path.join(HERE, 'matgraphs_tmp.npz')))
+        if out is None:
+            out = {k: d[k] for k in ('res', 'W2V', 'V2W', 'bias', 'bgcolor', 'light_dirs', 'light_colors', 'ambient', 'verts0', 'norms0',
+                                     'coors0', 'occup0', 'depth', 'flags', 'tex0', 'tex1')}
+            out['nspecs'] = np.int32(len(specs))
+        else:
+            assert np.array_equal(d['occup0'], out['occup0'])
+        out[f'spec{i}'] = np.array(spec)
+        out[f'image{i}'] = d['image_pre_tonemap']
+    os.remove(os.path.join(HERE, 'matgraphs_tmp.npz'))
+    np.savez_compressed(os.path.join(HERE, 'matgraphs_random.npz'), **out)
+    print('matgraphs_random:', len(specs), 'graphs;', os.path.getsize(os.path.join(HERE, 'matgraphs_random.npz')), 'B')
+
+
 if __name__ == '__main__':
     np.seterr(all='ignore')
     if len(sys.argv) > 1:  # python make_golden.py micro ...  -> only these cases
@@ -401,3 +491,5 @@ if __name__ == '__main__':
     case_particles()
     case_wireframe()
     case_postfx()
+    case_setup_cache()
+    case_matgraphs()

@@ -17,7 +17,7 @@ import scenes
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, '*.npz'))
-               if not os.path.basename(p).startswith('particles'))
+               if not os.path.basename(p).startswith(('particles', 'matgraphs')))
 COLOR_TOL = 2e-6
 
 
@@ -30,12 +30,16 @@ def _lighting(tina, g):
     return L
 
 
-def _material(tina, g, k):
-    ns = {n: getattr(tina, n) for n in ('PBR', 'Classic', 'Diffuse', 'Lamp', 'Lambert', 'Phong', 'Emission', 'CookTorrance', 'Texture')}
+MATERIAL_NAMES = ('PBR', 'Classic', 'Diffuse', 'Lamp', 'Lambert', 'Phong', 'Emission', 'CookTorrance', 'Texture', 'FresnelFactor',
+                  'MixMaterial', 'ScaleMaterial', 'AddMaterial')
+
+
+def _material(tina, g, k, key='material'):
+    ns = {n: getattr(tina, n) for n in MATERIAL_NAMES}
     for i in range(4):
         if f'tex{i}' in g:
             ns[f'tex{i}'] = g[f'tex{i}']
-    return eval(str(g[f'material{k}']), ns)
+    return eval(str(g[f'{key}{k}']), ns)
 
 
 def test_goldens_exist():
@@ -239,3 +243,37 @@ def test_oracle_ssao_matches_reference_sources(tina, O):
     assert g['ao'].max() > 0.3 and (g['ao'] > 0).sum() > 100
     assert np.array_equal(ao, g['ao'])
     assert np.array_equal(O.ssao_apply(g['image_before'], g['ao']), g['image_after'])
+
+
+def test_oracle_material_front_end_on_random_graphs(tina, O):
+    """36 random material graphs shaded by the reference's own matr/ + lighting sources (make_golden.py::case_matgraphs):
+    the oracle -- with its own flattener, oracle/materials.py -- reproduces every image to 2e-6."""
+    g = np.load(os.path.join(GOLDEN, 'matgraphs_random.npz'))
+    W, H = (int(v) for v in g['res'])
+    flags = int(g['flags'])
+    lighting = _lighting(tina, g)
+    assert int(g['nspecs']) >= 30 and len(g['light_dirs']) == 2
+    occup, depth, _, _ = O.render_occup(g['verts0'], g['W2V'], W, H, flags, g['bias'])
+    assert np.array_equal(occup, g['occup0']) and np.array_equal(depth, g['depth'])
+    kinds = set()
+    for i in range(int(g['nspecs'])):
+        image = np.zeros((W, H, 3), np.float32)
+        O.render_color(g['verts0'], g['norms0'], g['coors0'], occup, g['W2V'], g['V2W'], W, H, flags, _material(tina, g, i, 'spec'),
+                       lighting, image, g['bias'])
+        ref = g[f'image{i}']
+        err = (np.abs(image - ref) / np.maximum(1.0, np.abs(ref))).max()  # (sharp Cook-Torrance lobes reach ~30: 1 ulp there is 2e-6)
+        assert err <= COLOR_TOL, (i, str(g[f'spec{i}']), err)
+        kinds |= {n for n in MATERIAL_NAMES if n in str(g[f'spec{i}'])}
+    assert kinds >= {'MixMaterial', 'ScaleMaterial', 'AddMaterial', 'CookTorrance', 'Phong', 'Texture', 'FresnelFactor', 'PBR', 'Classic'}
+
+
+def test_oracle_setup_cache_matches_reference(O):
+    """TriangleRaster.bcn / can / boo / coo / wsc as the reference's render_occup stored them (triangle.py:127-131)."""
+    g = np.load(os.path.join(GOLDEN, 'setup_cache_monkey.npz'))
+    W, H = (int(v) for v in g['res'])
+    out, _ = O.face_setup(g['verts0'], g['W2V'], W, H, int(g['flags']))
+    ok = out[:, 0] != 0
+    ref = np.concatenate([g['bcn'], g['can'], g['boo'], g['coo'], g['wsc']], axis=1)
+    assert 300 < ok.sum() < len(ok)
+    assert np.array_equal(out[ok, 1:12], ref[ok])
+    assert not ref[~ok].any()  # rejected faces: never written

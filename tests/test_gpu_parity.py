@@ -454,7 +454,7 @@ def _golden_cases():
     import glob
     import os
     d = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
-    return sorted(p for p in glob.glob(os.path.join(d, '*.npz')) if not os.path.basename(p).startswith('particles'))
+    return sorted(p for p in glob.glob(os.path.join(d, '*.npz')) if not os.path.basename(p).startswith(('particles', 'matgraphs')))
 
 
 @pytest.mark.parametrize('path', _golden_cases(), ids=lambda p: p.split('/')[-1][:-4])
@@ -1350,3 +1350,65 @@ def test_meshmodel_validates_indices_and_normal_adapters_follow_vertices(tina, O
     ref = O.render_scene([(v[f], vn[f], None, tina.Classic())], W, H, view, proj, scene.lighting, _flags(O, smoothing=True), do_tonemap=False)
     assert np.abs(b - ref['image']).max() <= 5e-4  # (summation order of the per-vertex accumulation differs)
     assert np.abs(a - b).max() > 0.05
+
+
+def test_random_material_graphs_match_reference_golden(tina):
+    """The CUDA shading path (host flattening + folding + hoisting, specialised kernels or the interpreter) on the 36 random
+    material graphs shaded by the reference's own sources: colour within 1e-4, ids / depth equal."""
+    import os
+    import torch
+    from test_golden import GOLDEN, _lighting, _material
+    g = np.load(os.path.join(GOLDEN, 'matgraphs_random.npz'))
+    W, H = (int(v) for v in g['res'])
+    flags = int(g['flags'])
+    engine = tina.Engine((W, H))
+    engine.W2V[None], engine.V2W[None], engine.bias[None] = g['W2V'], g['V2W'], g['bias']
+    raster = tina.TriangleRaster(engine, smoothing=bool(flags & 1), texturing=bool(flags & 2))
+    mesh = tina.SimpleMesh()
+    mesh.set_face_verts(g['verts0'])
+    mesh.set_face_norms(g['norms0'])
+    mesh.set_face_coors(g['coors0'])
+    lighting = _lighting(tina, g)
+    worst = 0.0
+    for i in range(int(g['nspecs'])):
+        img = tina.Field(torch.zeros((W, H, 3), device='cuda'))
+        engine.clear_depth()
+        raster.set_object(mesh)
+        raster.render_occup()
+        raster.render_color(tina.Shader(img, lighting, _material(tina, g, i, 'spec')))
+        torch.cuda.synchronize()
+        if i == 0:
+            assert np.array_equal(raster.occup.to_numpy(), g['occup0']) and np.array_equal(engine.depth.to_numpy(), g['depth'])
+        ref = g[f'image{i}']
+        err = float((np.abs(img.to_numpy() - ref) / np.maximum(1.0, np.abs(ref))).max())  # (HDR highlights reach ~30 before the tonemap)
+        assert err <= COLOR_TOL, (i, str(g[f'spec{i}']), err)
+        worst = max(worst, err)
+    assert worst <= COLOR_TOL
+
+
+def test_setup_cache_fields_match_reference_golden(tina):
+    """raster.bcn / can / boo / coo / wsc (triangle.py:25-29), materialised on demand, equal what the reference's
+    render_occup stored -- through the expanded-array path and through the indexed (MeshModel) path."""
+    import os
+    import torch
+    from test_golden import GOLDEN
+    g = np.load(os.path.join(GOLDEN, 'setup_cache_monkey.npz'))
+    W, H = (int(v) for v in g['res'])
+    n = len(g['verts0'])
+    for indexed in (False, True):
+        engine = tina.Engine((W, H))
+        engine.W2V[None], engine.V2W[None], engine.bias[None] = g['W2V'], g['V2W'], g['bias']
+        raster = tina.TriangleRaster(engine, maxfaces=2048)
+        if indexed:
+            raster.set_object(tina.MeshModel(scenes.load_monkey()))
+        else:
+            mesh = tina.SimpleMesh(maxfaces=2048)
+            mesh.set_face_verts(g['verts0'])
+            raster.set_object(mesh)
+        engine.clear_depth()
+        raster.render_occup()
+        for k in ('bcn', 'can', 'boo', 'coo', 'wsc'):
+            out = getattr(raster, k).to_numpy()
+            assert out.shape == (2048, 3 if k == 'wsc' else 2)
+            assert np.array_equal(out[:n], g[k]), (indexed, k)
+            assert not out[n:].any()
