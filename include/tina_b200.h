@@ -162,7 +162,8 @@ int tina_raster_set_faces(TinaRaster *r, const float *verts, const float *norms,
 /* set_object for MeshModel (+MeshTransform, +MeshNoCulling/FlipCulling/FlipNormal):
  * mesh/model.py:56-73, mesh/trans.py:28-40, mesh/cull.py:6-57.
  * v [nverts,3], vt [*,2], vn [nnorms,3]; faces [N,3,3] int32 = [corner][v, vt, vn].
- * trans_host / trans_normal_host may be NULL.
+ * trans_host / trans_normal_host: ntrans 4x4 / 3x3 matrices of nested MeshTransform wrappers, innermost first, each
+ * applied with its own rounding like the reference's call chain (ntrans = 0 or NULL: none; at most 4).
  * mode bits: 1 = double sided (MeshNoCulling), 2 = flip winding (MeshFlipCulling),
  *            4 = negate normals (MeshFlipNormal).
  * Indexed sources are NOT expanded: a per-unique-vertex stage (world position / normal here, clip
@@ -170,11 +171,11 @@ int tina_raster_set_faces(TinaRaster *r, const float *verts, const float *norms,
  * stay valid until the next set_faces*.  tina_raster_materialize writes the expanded copies. */
 int tina_raster_set_faces_indexed(TinaRaster *r, const float *v, int64_t nverts, const float *vt, const float *vn,
                                   int64_t nnorms, const int32_t *faces, int64_t nfaces, const float *trans_host,
-                                  const float *trans_normal_host, uint32_t mode, void *stream);
+                                  const float *trans_normal_host, int ntrans, uint32_t mode, void *stream);
 /* set_object for MeshGrid (mesh/grid.py:26-58): pos [nx,ny,3]; recomputes the
  * per-vertex normals like MeshGrid.pre_compute, texcoords (i/(nx-1), j/(ny-1)). */
 int tina_raster_set_faces_grid(TinaRaster *r, const float *pos, int nx, int ny, const float *trans_host,
-                               const float *trans_normal_host, uint32_t mode, void *stream);
+                               const float *trans_normal_host, int ntrans, uint32_t mode, void *stream);
 /* triangle.py:89-131 */
 int tina_raster_render_occup(TinaRaster *r, void *stream);
 /* triangle.py:134-153 + shader.py:119-131 + lighting.py:84-98; image [W,H,3] f32 */

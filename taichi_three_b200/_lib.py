@@ -69,9 +69,9 @@ SIGNATURES = {
     'tina_raster_create': (_i, [C.POINTER(_vp), _vp, _i64, _u32]),
     'tina_raster_destroy': (_i, [_vp]),
     'tina_raster_set_faces': (_i, [_vp, _vp, _vp, _vp, _i64, _i, _vp]),
-    'tina_raster_set_faces_indexed': (_i, [_vp, _vp, _i64, _vp, _vp, _i64, _vp, _i64, _fp, _fp, _u32, _vp]),
+    'tina_raster_set_faces_indexed': (_i, [_vp, _vp, _i64, _vp, _vp, _i64, _vp, _i64, _fp, _fp, _i, _u32, _vp]),
     'tina_raster_materialize': (_i, [_vp, _vp]),
-    'tina_raster_set_faces_grid': (_i, [_vp, _vp, _i, _i, _fp, _fp, _u32, _vp]),
+    'tina_raster_set_faces_grid': (_i, [_vp, _vp, _i, _i, _fp, _fp, _i, _u32, _vp]),
     'tina_raster_render_occup': (_i, [_vp, _vp]),
     'tina_raster_render_color': (_i, [_vp, C.POINTER(TinaMaterial), C.POINTER(TinaLighting), _vp, _u32, _fp, _vp]),
     'tina_raster_render_color_range': (_i, [_vp, C.POINTER(TinaMaterial), C.POINTER(TinaLighting), _vp, _u32, _fp, _i64, _i64,

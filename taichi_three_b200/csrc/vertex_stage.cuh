@@ -4,11 +4,28 @@
 // ------------------------------------------------------------------------------------
 // K0: set_object adapters
 // ------------------------------------------------------------------------------------
+#define TINA_MAX_XFORMS 4 /* nested MeshTransform wrappers, applied innermost first like the reference's call chain */
 struct Xform {
-    float t[16];
-    float tn[9];
-    int has_t;
+    float t[TINA_MAX_XFORMS][16];
+    float tn[TINA_MAX_XFORMS][9];
+    int has_t; // number of transforms in the chain
 };
+// mesh/trans.py:28-40 for a chain of wrappers: one rounding sequence per wrapper, innermost first
+__device__ __forceinline__ void xform_pos(const Xform &X, float &a, float &b, float &c) {
+    for (int k = 0; k < X.has_t; k++) {
+        V3 r = mapply_pos3(X.t[k], a, b, c);
+        a = r.x, b = r.y, c = r.z;
+    }
+}
+__device__ __forceinline__ void xform_nrm(const Xform &X, float &a, float &b, float &c) { // trans_normal @ norm, not re-normalised
+    for (int k = 0; k < X.has_t; k++) {
+        const float *tn = X.tn[k];
+        const float ra = (tn[0] * a + tn[1] * b) + tn[2] * c;
+        const float rb = (tn[3] * a + tn[4] * b) + tn[5] * c;
+        const float rc = (tn[6] * a + tn[7] * b) + tn[8] * c;
+        a = ra, b = rb, c = rc;
+    }
+}
 
 // mesh/model.py:56-73 (+ trans.py:28-40, cull.py:6-57).  One thread per output corner.
 __global__ void k_gather_indexed(const float *__restrict__ v, const float *__restrict__ vt, const float *__restrict__ vn,
@@ -20,17 +37,14 @@ __global__ void k_gather_indexed(const float *__restrict__ v, const float *__res
     long long n = t / 3;
     int k = (int)(t - n * 3);
     long long src = (mode & 1u) ? (n >> 1) : n;
-    bool flip = (mode & 2u) || ((mode & 1u) && (n & 1));
+    bool flip = ((mode & 2u) != 0) != (((mode & 1u) != 0) && (n & 1)); // a flip around a double-sided wrapper un-reverses the odd copies
     bool neg = ((mode & 1u) && (n & 1)) != ((mode & 4u) != 0);
     int ks = flip ? 2 - k : k;
     const int32_t *fc = faces + (src * 3 + ks) * 3;
     {
         const float *p = v + (long long)(uint32_t)fc[0] * 3;
         float a = p[0], b = p[1], c = p[2];
-        if (X.has_t) {
-            V3 r = mapply_pos3(X.t, a, b, c);
-            a = r.x, b = r.y, c = r.z;
-        }
+        xform_pos(X, a, b, c);
         float *o = overts + t * 3;
         o[0] = a, o[1] = b, o[2] = c;
     }
@@ -41,12 +55,7 @@ __global__ void k_gather_indexed(const float *__restrict__ v, const float *__res
     if (onorms) {
         const float *p = vn + (long long)(uint32_t)fc[2] * 3;
         float a = p[0], b = p[1], c = p[2];
-        if (X.has_t) { // trans.py:38-40: trans_normal @ norm, not re-normalised
-            float ra = (X.tn[0] * a + X.tn[1] * b) + X.tn[2] * c;
-            float rb = (X.tn[3] * a + X.tn[4] * b) + X.tn[5] * c;
-            float rc = (X.tn[6] * a + X.tn[7] * b) + X.tn[8] * c;
-            a = ra, b = rb, c = rc;
-        }
+        xform_nrm(X, a, b, c);
         if (neg) a = -a, b = -b, c = -c;
         float *o = onorms + t * 3;
         o[0] = a, o[1] = b, o[2] = c;
@@ -76,7 +85,7 @@ __global__ void k_grid_faces(const float *__restrict__ pos, const float *__restr
     long long n = t / 3;
     int k = (int)(t - n * 3);
     long long src = (mode & 1u) ? (n >> 1) : n;
-    bool flip = (mode & 2u) || ((mode & 1u) && (n & 1));
+    bool flip = ((mode & 2u) != 0) != (((mode & 1u) != 0) && (n & 1)); // a flip around a double-sided wrapper un-reverses the odd copies
     bool neg = ((mode & 1u) && (n & 1)) != ((mode & 4u) != 0);
     int ks = flip ? 2 - k : k;
     const int stride = nx - 1; // sic (grid.py:46)
@@ -91,10 +100,7 @@ __global__ void k_grid_faces(const float *__restrict__ pos, const float *__restr
     long long vi = (long long)ci * ny + cj;
     {
         float a = pos[vi * 3], b = pos[vi * 3 + 1], c = pos[vi * 3 + 2];
-        if (X.has_t) {
-            V3 r = mapply_pos3(X.t, a, b, c);
-            a = r.x, b = r.y, c = r.z;
-        }
+        xform_pos(X, a, b, c);
         overts[t * 3] = a, overts[t * 3 + 1] = b, overts[t * 3 + 2] = c;
     }
     if (ocoors) { // grid.py:17-21: I / (res - 1)
@@ -103,12 +109,7 @@ __global__ void k_grid_faces(const float *__restrict__ pos, const float *__restr
     }
     if (onorms) {
         float a = nrm[vi * 3], b = nrm[vi * 3 + 1], c = nrm[vi * 3 + 2];
-        if (X.has_t) {
-            float ra = (X.tn[0] * a + X.tn[1] * b) + X.tn[2] * c;
-            float rb = (X.tn[3] * a + X.tn[4] * b) + X.tn[5] * c;
-            float rc = (X.tn[6] * a + X.tn[7] * b) + X.tn[8] * c;
-            a = ra, b = rb, c = rc;
-        }
+        xform_nrm(X, a, b, c);
         if (neg) a = -a, b = -b, c = -c;
         onorms[t * 3] = a, onorms[t * 3 + 1] = b, onorms[t * 3 + 2] = c;
     }
@@ -122,14 +123,14 @@ __global__ void k_vtx_world(const float *__restrict__ v, long long nv, const flo
                             const __grid_constant__ Xform X, float *__restrict__ vpos, float *__restrict__ vnrm) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t < nv) {
-        V3 r = mapply_pos3(X.t, v[t * 3], v[t * 3 + 1], v[t * 3 + 2]);
-        vpos[t * 3] = r.x, vpos[t * 3 + 1] = r.y, vpos[t * 3 + 2] = r.z;
+        float a = v[t * 3], b = v[t * 3 + 1], c = v[t * 3 + 2];
+        xform_pos(X, a, b, c);
+        vpos[t * 3] = a, vpos[t * 3 + 1] = b, vpos[t * 3 + 2] = c;
     }
     if (vnrm && t < nvn) {
-        const float a = vn[t * 3], b = vn[t * 3 + 1], c = vn[t * 3 + 2];
-        vnrm[t * 3] = (X.tn[0] * a + X.tn[1] * b) + X.tn[2] * c;
-        vnrm[t * 3 + 1] = (X.tn[3] * a + X.tn[4] * b) + X.tn[5] * c;
-        vnrm[t * 3 + 2] = (X.tn[6] * a + X.tn[7] * b) + X.tn[8] * c;
+        float a = vn[t * 3], b = vn[t * 3 + 1], c = vn[t * 3 + 2];
+        xform_nrm(X, a, b, c);
+        vnrm[t * 3] = a, vnrm[t * 3 + 1] = b, vnrm[t * 3 + 2] = c;
     }
 }
 
@@ -140,8 +141,9 @@ __global__ void k_pars_transform(const float *__restrict__ v, const float *__res
                                  const __grid_constant__ Xform X, float scale, float *__restrict__ ov, float *__restrict__ osz) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
-    V3 r = mapply_pos3(X.t, v[t * 3], v[t * 3 + 1], v[t * 3 + 2]);
-    ov[t * 3] = r.x, ov[t * 3 + 1] = r.y, ov[t * 3 + 2] = r.z;
+    float a = v[t * 3], b = v[t * 3 + 1], c = v[t * 3 + 2];
+    xform_pos(X, a, b, c);
+    ov[t * 3] = a, ov[t * 3 + 1] = b, ov[t * 3 + 2] = c;
     osz[t] = scale * sz[t];
 }
 

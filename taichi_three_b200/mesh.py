@@ -220,9 +220,14 @@ class MeshTransform(MeshEditBase):
 
     def _source(self):
         s = self.mesh._source()
-        if s.trans is not None:
-            raise NotImplementedError('nested MeshTransform is not supported: pre-multiply the matrices')
-        s.trans, s.trans_normal = self.trans, self.trans_normal
+        if s.trans is None:
+            s.trans, s.trans_normal = self.trans, self.trans_normal
+        else:  # nested MeshTransform: keep the chain (innermost first); the reference rounds after every wrapper
+            inner_t = s.trans if isinstance(s.trans, list) else [s.trans]
+            inner_n = s.trans_normal if isinstance(s.trans_normal, list) else [s.trans_normal]
+            if len(inner_t) >= 4:
+                raise NotImplementedError('more than four nested MeshTransform wrappers')
+            s.trans, s.trans_normal = inner_t + [self.trans], inner_n + [self.trans_normal]
         return s
 
 
@@ -231,8 +236,8 @@ class MeshFlipCulling(MeshEditBase):
 
     def _source(self):
         s = self.mesh._source()
-        if s.double_sided:
-            raise NotImplementedError('MeshFlipCulling(MeshNoCulling(...)) is not supported')
+        # (around a MeshNoCulling the even copies end up reversed and the odd, normal-negated copies in the original
+        # order -- cull.py:17-27 over :40-57 -- which is what mode bits 1 | 2 select in corner_ids)
         s.flip = not s.flip
         return s
 

@@ -65,8 +65,12 @@ class TriangleRaster:
         total = n * (2 if s.double_sided else 1)
         if total > self.maxfaces:
             raise ValueError(f'{total} faces exceed maxfaces={self.maxfaces}: pass maxfaces=... to Scene / TriangleRaster')
-        trans = _fp(s.trans) if s.trans is not None else None
-        tn = _fp(s.trans_normal) if s.trans is not None else None
+        # nested MeshTransform wrappers: a chain of matrices, innermost first (each applied with its own rounding)
+        chain = s.trans if isinstance(s.trans, list) else ([s.trans] if s.trans is not None else [])
+        nchain = s.trans_normal if isinstance(s.trans_normal, list) else ([s.trans_normal] if s.trans is not None else [])
+        ntrans = len(chain)
+        trans = _fp(np.stack(chain)) if ntrans else None
+        tn = _fp(np.stack(nchain)) if ntrans else None
         keep = []
         if s.kind == 'simple' and s.trans is None and s.mode == 0:
             v, nn, tt = s.verts, s.norms if self.smoothing else None, s.coors if self.texturing else None
@@ -95,11 +99,11 @@ class TriangleRaster:
             ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
             _lib.check(L.tina_raster_set_faces_indexed(self._h, ptr(v), v.shape[0], ptr(vt) if self.texturing else None,
                                                        ptr(vn) if self.smoothing else None,
-                                                       vn.shape[0] if vn is not None else 0, ptr(faces), n, trans, tn,
+                                                       vn.shape[0] if vn is not None else 0, ptr(faces), n, trans, tn, ntrans,
                                                        s.mode, st))
         elif s.kind == 'grid':
             keep = [s.pos]
-            _lib.check(L.tina_raster_set_faces_grid(self._h, C.c_void_p(s.pos.data_ptr()), s.nx, s.ny, trans, tn, s.mode, st))
+            _lib.check(L.tina_raster_set_faces_grid(self._h, C.c_void_p(s.pos.data_ptr()), s.nx, s.ny, trans, tn, ntrans, s.mode, st))
         else:
             raise ValueError(s.kind)
         self._keep = keep

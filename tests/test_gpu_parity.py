@@ -1412,3 +1412,50 @@ def test_setup_cache_fields_match_reference_golden(tina):
             assert out.shape == (2048, 3 if k == 'wsc' else 2)
             assert np.array_equal(out[:n], g[k]), (indexed, k)
             assert not out[n:].any()
+
+
+def test_nested_mesh_wrappers(tina, O):
+    """Wrappers compose freely in the reference (mesh/trans.py:28-40, mesh/cull.py:5-66): MeshTransform inside MeshTransform
+    (one rounding sequence per wrapper, NOT the product matrix), MeshFlipCulling around MeshNoCulling and the other way
+    round, on a MeshModel and on a MeshGrid; raster.verts / norms equal the oracle's providers bit for bit and the frame
+    equals the oracle's."""
+    import torch
+    W, H = 200, 150
+    view, proj = tina.orbit_camera(radius=3.2, theta=0.3, phi=0.5, aspect=W / H)
+    t1 = tina.translate([0.13, -0.21, 0.07]) @ tina.eularXYZ([0.41, -0.33, 0.27]) @ tina.scale([1.31, 0.77, 1.13])
+    t2 = tina.eularXYZ([-0.2, 0.6, 0.1]) @ tina.scale(0.83) @ tina.translate([0.05, 0.02, -0.11])
+    obj = scenes.load_monkey()
+    v, vn, vt = O.indexed(obj)
+    v1, n1 = O.transform(v, vn, t1)
+    v2, n2 = O.transform(v1, n1, t2)
+    # (a) nested transforms, then flip-culling around no-culling
+    fv, fn, _ = O.no_culling(v2, n2)
+    fv, fn = np.ascontiguousarray(fv[:, ::-1]), np.ascontiguousarray(fn[:, ::-1])
+    for order in ('flip_outside', 'flip_inside'):
+        base = tina.MeshTransform(tina.MeshTransform(tina.MeshModel(obj), t1), t2)
+        mesh = tina.MeshFlipCulling(tina.MeshNoCulling(base)) if order == 'flip_outside' else tina.MeshNoCulling(tina.MeshFlipCulling(base))
+        scene = tina.Scene((W, H), smoothing=True, maxfaces=4096)
+        scene.add_object(mesh, tina.Classic())
+        scene.engine.set_camera(view, proj)
+        scene.render()
+        torch.cuda.synchronize()
+        assert np.array_equal(scene.triangle_raster.verts.to_numpy(), fv), order
+        assert np.array_equal(scene.triangle_raster.norms.to_numpy(), fn), order
+        ref = O.render_scene([(fv, fn, None, tina.Classic())], W, H, view, proj, scene.lighting, _flags(O, smoothing=True))
+        _check_frame(scene, ref)
+    # the product matrix is a different computation: the chain must not be collapsed
+    vp, _ = O.transform(v, vn, t2 @ t1)
+    assert not np.array_equal(vp, v2)
+    # (b) a grid inside two transforms
+    n = 40
+    pos = scenes.wave_grid_pos(n)
+    grid = tina.MeshGrid(n)
+    grid.pos.from_numpy(pos)
+    scene = tina.Scene((W, H), smoothing=True)
+    scene.add_object(tina.MeshTransform(tina.MeshTransform(grid, t2), t1), tina.Classic())
+    scene.engine.set_camera(view, proj)
+    scene.render()
+    gv, gn = O.transform(*O.transform(O.grid_faces(pos), O.grid_faces(O.grid_normals(pos)), t2), t1)
+    ref = O.render_scene([(gv, gn, None, tina.Classic())], W, H, view, proj, scene.lighting, _flags(O, smoothing=True))
+    _check_frame(scene, ref)
+    assert np.array_equal(scene.triangle_raster.verts.to_numpy(), gv)
