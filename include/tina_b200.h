@@ -51,6 +51,8 @@ typedef struct TinaRaster TinaRaster;
 /* tina_render_color flags */
 #define TINA_COLOR_TONEMAP 1u /* fuse aces_tonemap (advans.py:32-35) into the store            */
 #define TINA_COLOR_FILL_BG 2u /* also write `bg` to pixels this object does not own (raster.py:176) */
+#define TINA_COLOR_FINISH 4u  /* last shading pass of a multi-object frame: pixels this object does not own are read back and
+                               * finished too (tonemapped if TINA_COLOR_TONEMAP is set, accumulated if an accumulator is given) */
 
 #define TINA_MAX_LIGHTS 16 /* lighting.py:26 */
 #define TINA_MAX_INSTR 96
@@ -181,6 +183,11 @@ int tina_raster_render_occup(TinaRaster *r, void *stream);
 /* triangle.py:134-153 + shader.py:119-131 + lighting.py:84-98; image [W,H,3] f32 */
 int tina_raster_render_color(TinaRaster *r, const TinaMaterial *mat_host, const TinaLighting *light_host,
                              float *image, uint32_t flags, const float *bg_host, void *stream);
+/* the same with the frame's TAA accumulation (util/accumator.py:16-23: acc = acc * (1 - 1/count) + image * (1/count)) fused
+ * into the pass: needs TINA_COLOR_FILL_BG (single-object frame) or TINA_COLOR_FINISH (last object), i.e. a pass that
+ * visits every pixel; acc [W,H,3] f32, count >= 1 */
+int tina_raster_render_color_accumulate(TinaRaster *r, const TinaMaterial *mat_host, const TinaLighting *light_host, float *image,
+                                        uint32_t flags, const float *bg_host, float *acc, int count, void *stream);
 /* render_color restricted to pixels [first_pixel, first_pixel + npixels) (first_pixel a multiple of 256) of
  * the CURRENT face arrays with an explicit id offset: after a sort-last key composite every rank shades
  * one screen strip from the replicated attributes (face_base = 0). */

@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('TINA_B200_LIB') or os.path.join(_HERE, 'csrc', 'libtina_b200.so')  # env: kernel-variant experiments
 
 TINA_SMOOTHING, TINA_TEXTURING, TINA_CULLING, TINA_CLIPPING = 1, 2, 4, 8
-TINA_COLOR_TONEMAP, TINA_COLOR_FILL_BG = 1, 2
+TINA_COLOR_TONEMAP, TINA_COLOR_FILL_BG, TINA_COLOR_FINISH = 1, 2, 4
 TINA_MAX_LIGHTS, TINA_MAX_INSTR, TINA_MAX_TEX = 16, 96, 4
 
 (OP_CONST, OP_INPUT, OP_TEXTURE, OP_FRESNEL, OP_LAMBERT, OP_PHONG, OP_COOK, OP_MIX, OP_MUL,
@@ -74,6 +74,7 @@ SIGNATURES = {
     'tina_raster_set_faces_grid': (_i, [_vp, _vp, _i, _i, _fp, _fp, _i, _u32, _vp]),
     'tina_raster_render_occup': (_i, [_vp, _vp]),
     'tina_raster_render_color': (_i, [_vp, C.POINTER(TinaMaterial), C.POINTER(TinaLighting), _vp, _u32, _fp, _vp]),
+    'tina_raster_render_color_accumulate': (_i, [_vp, C.POINTER(TinaMaterial), C.POINTER(TinaLighting), _vp, _u32, _fp, _vp, _i, _vp]),
     'tina_raster_render_color_range': (_i, [_vp, C.POINTER(TinaMaterial), C.POINTER(TinaLighting), _vp, _u32, _fp, _i64, _i64,
                                              _u32, _vp]),
     'tina_raster_render_color_composite': (_i, [_vp, C.POINTER(TinaMaterial), C.POINTER(TinaLighting), _vp, _u32, _fp, _i64,

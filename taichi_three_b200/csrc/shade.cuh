@@ -592,7 +592,8 @@ k_render_color(const long long *__restrict__ keys, const float *__restrict__ ver
                float *__restrict__ image, uint32_t cflags, float bg0, float bg1, float bg2,
                const __grid_constant__ Src S, const unsigned char *__restrict__ blkflags, unsigned *__restrict__ publish,
                const unsigned *__restrict__ counters, int pix_lo, int pix_hi, unsigned *__restrict__ pubstate,
-               unsigned char flagval, const __grid_constant__ PeerTab peers, long long *__restrict__ keys_out) {
+               unsigned char flagval, const __grid_constant__ PeerTab peers, long long *__restrict__ keys_out,
+               float *__restrict__ acc, int acc_count) {
     static_assert(K4_THREADS == (1 << FLAG_SHIFT), "one coverage flag per K4 block");
     pdl_wait();
     if (blockIdx.x == 0 && threadIdx.x == 0 && publish) { // tell the host how many faces needed the tile path
@@ -606,8 +607,29 @@ k_render_color(const long long *__restrict__ keys, const float *__restrict__ ver
     }
     const int npix = pix_hi; // this launch shades pixels [pix_lo, pix_hi); pix_lo is a multiple of 256
     const bool fill = (cflags & TINA_COLOR_FILL_BG) != 0;
+    // TINA_COLOR_FINISH: the frame's last shading pass also finishes the pixels it does not own (tonemap + TAA
+    // accumulation, scene/raster.py:202-207) instead of leaving them to separate full-screen passes
+    const bool finish = (cflags & TINA_COLOR_FINISH) != 0 && !fill;
     float r = bg0, g = bg1, b = bg2;
     if (fill && (cflags & TINA_COLOR_TONEMAP)) r = aces(r), g = aces(g), b = aces(b);
+    // util/accumator.py:16-23 for one pixel (the same f32 operations as k_accumulate)
+    auto accumulate = [&](long long P_, float cr, float cg, float cb) {
+        const float inv = __fdiv_rn(1.0f, (float)acc_count), keep = __fsub_rn(1.0f, inv);
+        float *a = acc + P_ * 3;
+        a[0] = __fadd_rn(__fmul_rn(a[0], keep), __fmul_rn(cr, inv));
+        a[1] = __fadd_rn(__fmul_rn(a[1], keep), __fmul_rn(cg, inv));
+        a[2] = __fadd_rn(__fmul_rn(a[2], keep), __fmul_rn(cb, inv));
+    };
+    // a pixel of another object (or the background) in the frame's last pass
+    auto finish_pixel = [&](long long P_) {
+        float *o = image + P_ * 3;
+        float cr = o[0], cg = o[1], cb = o[2];
+        if (cflags & TINA_COLOR_TONEMAP) {
+            cr = aces(cr), cg = aces(cg), cb = aces(cb);
+            o[0] = cr, o[1] = cg, o[2] = cb;
+        }
+        if (acc) accumulate(P_, cr, cg, cb);
+    };
     // (CTAs take the chunks in plain order: spreading covered and background chunks over the launch -- CTA b -> chunk
     // (b % 8) * n / 8 + b / 8 -- measured 1.3 us slower on C2, profiles/r2_k4_variants.md)
     const unsigned chunk = blockIdx.x;
@@ -616,10 +638,18 @@ k_render_color(const long long *__restrict__ keys, const float *__restrict__ ver
     // any other value holds none of its pixels.  flagval == 0: only "nothing rasterised here since the clear" is known.
     const unsigned char cf = blkflags ? blkflags[(pix_lo >> FLAG_SHIFT) + chunk] : (unsigned char)1;
     if (blkflags && (flagval ? cf != flagval : cf == 0)) {
-        if (fill) {
+        if (finish) {
+            if (p0 + threadIdx.x < npix) finish_pixel(p0 + threadIdx.x);
+        } else if (fill) {
             const int np = (int)min((long long)K4_THREADS, (long long)npix - p0);
             const int t = threadIdx.x;
-            if (np == K4_THREADS && (((uintptr_t)image) & 15) == 0) { // 3072 contiguous, 16-byte aligned bytes: 192 float4 stores
+            if (acc) { // background + accumulation: per-pixel read-modify-write of the accumulator
+                if (t < np) {
+                    float *out = image + (p0 + t) * 3;
+                    out[0] = r, out[1] = g, out[2] = b;
+                    accumulate(p0 + t, r, g, b);
+                }
+            } else if (np == K4_THREADS && (((uintptr_t)image) & 15) == 0) { // 3072 contiguous, 16-byte aligned bytes: 192 float4 stores
                 if (t < 192) {
                     const int m = t % 3;
                     const float4 v = m == 0 ? make_float4(r, g, b, r) : m == 1 ? make_float4(g, b, r, g) : make_float4(b, r, g, b);
@@ -654,12 +684,18 @@ k_render_color(const long long *__restrict__ keys, const float *__restrict__ ver
     const unsigned fid = id - 1u - base;
     float *out = image + (long long)P * 3;
     if (id == 0u || fid >= nfaces) { // triangle.py:137-138 (occup == -1)
-        if (fill) __stcs(out, r), __stcs(out + 1, g), __stcs(out + 2, b);
+        if (finish) {
+            finish_pixel(P);
+        } else if (fill) {
+            __stcs(out, r), __stcs(out + 1, g), __stcs(out + 2, b);
+            if (acc) accumulate(P, r, g, b);
+        }
         return;
     }
     V3 c = shade_pixel<KIND, IDX, FAST, LEAN>(P, fid, verts, norms, coors, cam, flags, mat, L, S);
     if (cflags & TINA_COLOR_TONEMAP) c.x = aces_t<FAST>(c.x), c.y = aces_t<FAST>(c.y), c.z = aces_t<FAST>(c.z);
     __stcs(out, c.x), __stcs(out + 1, c.y), __stcs(out + 2, c.z);
+    if (acc) accumulate(P, c.x, c.y, c.z);
 }
 
 // G-buffer sinks (core/shader.py:21-109, probe.py:21-23): attributes of the visible surface per pixel.  One launch

@@ -140,16 +140,27 @@ class Scene:
         bg = np.broadcast_to(np.asarray(self.bgcolor, dtype=np.float32), (3,))
         if not items:
             self.image.fill(bg)
-        def fuses(raster):  # rasterisers whose render_color takes the fill / tonemap fusion hints
-            return isinstance(raster, TriangleRaster) or hasattr(raster, 'set_particles')
-        # the ACES curve rides along only when the frame's single object is shaded by a pass that applies it
-        # (a wireframe-only scene is tonemapped by the separate pass below, like every multi-object frame)
-        fuse_tm = bool(self.tonemap) and len(items) == 1 and not self.blooming and not self.ssao and fuses(items[0][1].raster)
+        def fuses(raster):  # rasterisers whose render_color takes the fusion hints
+            return isinstance(raster, TriangleRaster)
+        # Frame glue folded into the shading passes (results identical to the separate passes):
+        #  * image.fill(bg) rides along with the FIRST object's pass (every rasteriser that takes fill_bg);
+        #  * the ACES curve and the TAA accumulation ride along with the LAST object's pass when that is a triangle pass
+        #    and nothing sits between shading and tonemap (no SSAO / blooming): it finishes the pixels it does not own too.
+        post_free = not self.blooming and not self.ssao and getattr(self, 'fuse_glue', True)  # (fuse_glue = False: separate passes)
+        last_fuses = bool(items) and fuses(items[-1][1].raster) and post_free
+        fuse_tm = bool(self.tonemap) and (last_fuses or (len(items) == 1 and post_free and hasattr(items[0][1].raster, 'set_particles')))
+        fuse_acc = bool(self.taa) and last_fuses and not self.fxaa
+        if fuse_acc:
+            self.accum.count[0] += 1
         for i, (obj, info) in enumerate(items):
             shader = self.shaders[id(info.material)]
             info.raster.set_object(obj)
             info.raster.render_occup()
+            last = i == len(items) - 1
             if fuses(info.raster):
+                info.raster.render_color(shader, fill_bg=bg if i == 0 else None, tonemap=fuse_tm and last, finish=last and (fuse_tm or fuse_acc),
+                                         accum=(self.accum.img.to_torch(), self.accum.count[0]) if (fuse_acc and last) else None)
+            elif hasattr(info.raster, 'set_particles'):
                 info.raster.render_color(shader, fill_bg=bg if i == 0 else None, tonemap=fuse_tm)
             else:
                 if i == 0:
@@ -165,7 +176,7 @@ class Scene:
             _lib.check(_lib.lib().tina_image_tonemap(C.c_void_p(t.data_ptr()), t.numel(), _stream()))
         if self.fxaa:  # raster.py:204-205
             self.fxaa.apply(self.image)
-        if self.taa:  # raster.py:206-207
+        if self.taa and not fuse_acc:  # raster.py:206-207
             self.accum.update(self.pp_img)
 
     @property

@@ -137,10 +137,14 @@ class TriangleRaster:
         self._occup_stale = True
 
     # ---- render_color (triangle.py:134-153) --------------------------------------------
-    def render_color(self, shader, fill_bg=None, tonemap=False):
-        """`shader`: a Shader or a ShaderGroup of Shaders.  fill_bg / tonemap are fusion hints used by Scene.render."""
+    def render_color(self, shader, fill_bg=None, tonemap=False, finish=False, accum=None):
+        """`shader`: a Shader or a ShaderGroup of Shaders.  Fusion hints used by Scene.render: fill_bg = also write the
+        background to the pixels this object does not own (first object), tonemap = ACES on what the pass writes,
+        finish = last object of a multi-object frame: pixels of the other objects are read back and tonemapped too,
+        accum = (accumulator tensor [W,H,3], count): the frame's TAA accumulation (needs fill_bg or finish)."""
         shaders = shader.shaders if isinstance(shader, ShaderGroup) else (shader,)
-        flags = (_lib.TINA_COLOR_TONEMAP if tonemap else 0) | (_lib.TINA_COLOR_FILL_BG if fill_bg is not None else 0)
+        flags = ((_lib.TINA_COLOR_TONEMAP if tonemap else 0) | (_lib.TINA_COLOR_FILL_BG if fill_bg is not None else 0) |
+                 (_lib.TINA_COLOR_FINISH if finish and fill_bg is None else 0))
         bg = None
         if fill_bg is not None:
             key, bg = self._bg_cache
@@ -168,7 +172,11 @@ class TriangleRaster:
                 rec = (s, img, t, C.c_void_p(t.data_ptr()))
                 self._shader_cache[id(s)] = rec
             mat, keep = self._material_struct(s.material)
-            rc = self._color_fn(self._h, mat, s.lighting.struct_ref(), rec[3], flags, bg, st)
+            if accum is not None:
+                rc = _lib.lib().tina_raster_render_color_accumulate(self._h, mat, s.lighting.struct_ref(), rec[3], flags, bg,
+                                                                    C.c_void_p(accum[0].data_ptr()), int(accum[1]), st)
+            else:
+                rc = self._color_fn(self._h, mat, s.lighting.struct_ref(), rec[3], flags, bg, st)
             if rc:
                 _lib.check(rc)
             self._mat_keep = keep

@@ -1459,3 +1459,49 @@ def test_nested_mesh_wrappers(tina, O):
     ref = O.render_scene([(gv, gn, None, tina.Classic())], W, H, view, proj, scene.lighting, _flags(O, smoothing=True))
     _check_frame(scene, ref)
     assert np.array_equal(scene.triangle_raster.verts.to_numpy(), gv)
+
+
+def test_frame_glue_fused_into_the_last_shading_pass(tina, O):
+    """in a multi-object frame the ACES curve and the TAA accumulation ride along with the LAST object's
+    shading pass (it finishes the pixels of the other objects and the background too), the fill with the first one's and
+    the depth clear with the vertex stage.  Same images as the separate full-screen passes (scene.fuse_glue = False), and
+    fewer launches."""
+    import torch
+    from taichi_three_b200 import _lib
+    W, H = 192, 144
+    view, proj = scenes.default_camera(W / H)
+    a = scenes.soup(300, W, H, s=0.06, seed=21)
+    obj = scenes.load_monkey()
+
+    def run(fuse, taa, frames=3):
+        np.random.seed(5)  # the TAA jitter (engine.py:31-39)
+        scene = tina.Scene((W, H), taa=taa, bgcolor=[0.2, 0.1, 0.3])
+        scene.fuse_glue = fuse
+        m = tina.SimpleMesh()
+        m.set_face_verts(a)
+        scene.add_object(m, tina.Diffuse(color=[0.9, 0.5, 0.2]))
+        scene.add_object(tina.MeshModel(obj), tina.Classic())
+        scene.engine.set_camera(view, proj)
+        l0 = _lib.lib().tina_launch_count()
+        for _ in range(frames):
+            scene.render()
+        torch.cuda.synchronize()
+        return scene.img.to_numpy().copy(), scene.image.to_numpy().copy(), (_lib.lib().tina_launch_count() - l0) / frames
+    for taa in (False, True):
+        img_f, raw_f, n_f = run(True, taa)
+        img_s, raw_s, n_s = run(False, taa)
+        assert np.abs(img_f - img_s).max() <= 2e-6, taa
+        assert np.abs(raw_f - raw_s).max() <= 2e-6, taa
+        assert n_f <= n_s - (2 if taa else 1), (taa, n_f, n_s)
+    # and against the oracle (no TAA: centred samples)
+    scene = tina.Scene((W, H), bgcolor=[0.2, 0.1, 0.3])
+    m = tina.SimpleMesh()
+    m.set_face_verts(a)
+    scene.add_object(m, tina.Diffuse(color=[0.9, 0.5, 0.2]))
+    v, _, _ = O.indexed(obj)
+    scene.add_object(tina.MeshModel(obj), tina.Classic())
+    scene.engine.set_camera(view, proj)
+    scene.render()
+    ref = O.render_scene([(a, None, None, tina.Diffuse(color=[0.9, 0.5, 0.2])), (v, None, None, tina.Classic())], W, H, view, proj,
+                         scene.lighting, _flags(O), bgcolor=[0.2, 0.1, 0.3])
+    _check_frame(scene, ref)
