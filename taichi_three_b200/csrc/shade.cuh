@@ -584,7 +584,9 @@ struct PeerTab {
     int n, self;
 };
 
-template <int KIND, bool IDX, bool FAST, int LEAN = 0>
+// GLUE: the instantiations that can finish other objects' pixels (TINA_COLOR_FINISH) and accumulate (TAA); the
+// plain ones compile those paths away (carrying them as run-time options cost the C2 frame 2 us).
+template <int KIND, bool IDX, bool FAST, int LEAN = 0, bool GLUE = false>
 __global__ void __launch_bounds__(K4_THREADS, K4_MINBLOCKS)
 k_render_color(const long long *__restrict__ keys, const float *__restrict__ verts, const float *__restrict__ norms,
                const float *__restrict__ coors, const __grid_constant__ Cam cam, uint32_t flags, unsigned base,
@@ -593,8 +595,9 @@ k_render_color(const long long *__restrict__ keys, const float *__restrict__ ver
                const __grid_constant__ Src S, const unsigned char *__restrict__ blkflags, unsigned *__restrict__ publish,
                const unsigned *__restrict__ counters, int pix_lo, int pix_hi, unsigned *__restrict__ pubstate,
                unsigned char flagval, const __grid_constant__ PeerTab peers, long long *__restrict__ keys_out,
-               float *__restrict__ acc, int acc_count) {
+               float *__restrict__ acc_rt, int acc_count) {
     static_assert(K4_THREADS == (1 << FLAG_SHIFT), "one coverage flag per K4 block");
+    float *const acc = GLUE ? acc_rt : nullptr;
     pdl_wait();
     if (blockIdx.x == 0 && threadIdx.x == 0 && publish) { // tell the host how many faces needed the tile path
         // running counts live in device memory; the mapped host words are only written (posted stores, no PCIe
@@ -609,7 +612,7 @@ k_render_color(const long long *__restrict__ keys, const float *__restrict__ ver
     const bool fill = (cflags & TINA_COLOR_FILL_BG) != 0;
     // TINA_COLOR_FINISH: the frame's last shading pass also finishes the pixels it does not own (tonemap + TAA
     // accumulation, scene/raster.py:202-207) instead of leaving them to separate full-screen passes
-    const bool finish = (cflags & TINA_COLOR_FINISH) != 0 && !fill;
+    const bool finish = GLUE && (cflags & TINA_COLOR_FINISH) != 0 && !fill;
     float r = bg0, g = bg1, b = bg2;
     if (fill && (cflags & TINA_COLOR_TONEMAP)) r = aces(r), g = aces(g), b = aces(b);
     // util/accumator.py:16-23 for one pixel (the same f32 operations as k_accumulate)
@@ -637,6 +640,12 @@ k_render_color(const long long *__restrict__ keys, const float *__restrict__ ver
     // flagval != 0: this object's render_occup was the engine's last, its flags carry its own stamp -> a chunk with
     // any other value holds none of its pixels.  flagval == 0: only "nothing rasterised here since the clear" is known.
     const unsigned char cf = blkflags ? blkflags[(pix_lo >> FLAG_SHIFT) + chunk] : (unsigned char)1;
+#ifdef K4_SPECULATIVE_KEY
+    // the key is requested together with the coverage flag (one exposed round trip instead of two for covered chunks;
+    // for untouched chunks the load is wasted on L2-resident, just-cleared keys)
+    long long key_spec = 0;
+    if (peers.n <= 1 && p0 + threadIdx.x < npix) key_spec = __ldcs(keys + p0 + threadIdx.x);
+#endif
     if (blkflags && (flagval ? cf != flagval : cf == 0)) {
         if (finish) {
             if (p0 + threadIdx.x < npix) finish_pixel(p0 + threadIdx.x);
@@ -679,7 +688,11 @@ k_render_color(const long long *__restrict__ keys, const float *__restrict__ ver
         keys_out[P] = k;
         id = (unsigned)(unsigned long long)k;
     } else {
+#ifdef K4_SPECULATIVE_KEY
+        id = (unsigned)(unsigned long long)key_spec;
+#else
         id = (unsigned)(unsigned long long)__ldcs(keys + P);
+#endif
     }
     const unsigned fid = id - 1u - base;
     float *out = image + (long long)P * 3;
