@@ -640,12 +640,6 @@ k_render_color(const long long *__restrict__ keys, const float *__restrict__ ver
     // flagval != 0: this object's render_occup was the engine's last, its flags carry its own stamp -> a chunk with
     // any other value holds none of its pixels.  flagval == 0: only "nothing rasterised here since the clear" is known.
     const unsigned char cf = blkflags ? blkflags[(pix_lo >> FLAG_SHIFT) + chunk] : (unsigned char)1;
-#ifdef K4_SPECULATIVE_KEY
-    // the key is requested together with the coverage flag (one exposed round trip instead of two for covered chunks;
-    // for untouched chunks the load is wasted on L2-resident, just-cleared keys)
-    long long key_spec = 0;
-    if (peers.n <= 1 && p0 + threadIdx.x < npix) key_spec = __ldcs(keys + p0 + threadIdx.x);
-#endif
     if (blkflags && (flagval ? cf != flagval : cf == 0)) {
         if (finish) {
             if (p0 + threadIdx.x < npix) finish_pixel(p0 + threadIdx.x);
@@ -688,11 +682,7 @@ k_render_color(const long long *__restrict__ keys, const float *__restrict__ ver
         keys_out[P] = k;
         id = (unsigned)(unsigned long long)k;
     } else {
-#ifdef K4_SPECULATIVE_KEY
-        id = (unsigned)(unsigned long long)key_spec;
-#else
         id = (unsigned)(unsigned long long)__ldcs(keys + P);
-#endif
     }
     const unsigned fid = id - 1u - base;
     float *out = image + (long long)P * 3;
