@@ -237,11 +237,14 @@ extern "C" int tina_selftest_division(int device, uint64_t nquotients, uint64_t 
 // ------------------------------------------------------------------------------------
 // small full-screen kernels
 // ------------------------------------------------------------------------------------
-__global__ void k_clear_keys(long long *keys, int n, unsigned char *blkflags) {
+// one 256-thread block per 256-pixel coverage chunk; selective: chunks nobody wrote since the last clear (flag 0) are skipped
+__global__ void k_clear_keys(long long *keys, int n, unsigned char *blkflags, int selective) {
     pdl_launch_dependents(); // let the next kernel's launch overlap this one (it waits before touching memory)
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (selective && blkflags[blockIdx.x] == 0) return;
     if (i < n) keys[i] = (long long)MAXDEPTH_I << 32; // engine.py:68-70, winner = none
-    if (i <= (n >> FLAG_SHIFT)) blkflags[i] = 0;
+    __syncthreads(); // (every thread has read the flag)
+    if (threadIdx.x == 0) blkflags[blockIdx.x] = 0;
 }
 __global__ void k_depth(const long long *keys, int32_t *depth, int n) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
