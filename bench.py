@@ -38,7 +38,7 @@ sys.path.insert(0, os.path.join(ROOT, 'tests'))
 
 import numpy as np  # noqa: E402
 
-K1_NCU = 'r2_v1_k_raster_indexed_block_ncu.txt'
+K1_NCU = 'r2_v2_k_raster_indexed_ncu.txt'
 
 
 def ncu_traffic(kernel_file=K1_NCU):
@@ -621,7 +621,7 @@ def run_ours(args):
             'roofline': {'bound': 'hbm', 'kernel': 'k_raster_indexed', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                          'frac': achieved / peak, 'traffic': ncu_traffic() if wl == 'c2' else None,
                          'traffic_source': f'profiles/{K1_NCU} (ncu --set full, cold cache, dram read+write per launch)',
-                         'note': 'latency / occupancy-bound kernel: ncu smsp__issue_active 68 %, long-scoreboard 3.9 cycles per issue, DRAM 14 % of peak (same file)',
+                         'note': 'latency / occupancy-bound kernel: ncu smsp__issue_active 66 %, long-scoreboard 4.0 cycles per issue, DRAM 14 % of peak (same file)',
                          'alg_bytes': k1_bytes, 'peak_source': peak_src},
             'cpu_baseline': cpu,
             'e2e': {'value': e2e_value, 'unit': unit, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
