@@ -274,7 +274,9 @@ int tina_raster_buffers(TinaRaster *r, const float **verts, const float **norms,
  * 15 = indexed sources: mark every vertex record "not tame", so that every face takes the rasteriser's general
  *      path (float bounding box, x86 conversions, no tightening) instead of the per-vertex integer bounds,
  * 16 = plain square MeshGrid sources: independent persistent warps over row chunks staged through shared memory by
- *      cp.async (k_raster_grid; default 0: measured slower than the gather kernel every indexed source uses) */
+ *      cp.async (k_raster_grid; default 0: measured slower than the gather kernel every indexed source uses),
+ * 17 = plain square MeshGrid sources: one quad (two faces, four vertex records) per thread (k_raster_quads, default 1);
+ *      0 = one face per thread like every other indexed source */
 int tina_raster_set_tuning(TinaRaster *r, int which, int value);
 /* counters of the last render_occup (synchronises): faces culled, clipped, per-thread,
  * per-warp, queued for the tile path, tile-list entries */

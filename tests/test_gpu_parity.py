@@ -1134,8 +1134,9 @@ def test_deferred_clear_depth_semantics(tina, O):
 
 @pytest.mark.parametrize('n,W,H', [(160, 96, 64), (300, 640, 360), (131, 200, 136), (5, 64, 48)])
 def test_grid_tile_rasteriser_equals_gather_kernel(tina, O, n, W, H):
-    """k_raster_grid (knob grid_tiles: independent persistent warps over row chunks staged by cp.async) must give the
-    bits of the gather kernel and of the oracle: chunks per row that divide / do not divide the row, more chunks than
+    """The three rasterisers a plain square MeshGrid can take -- k_raster_quads (default: one quad = two faces per thread),
+    k_raster_indexed (grid_quads=0: one face per thread, what every other indexed source uses) and k_raster_grid (knob
+    grid_tiles: persistent warps over row chunks staged by cp.async) -- must give the same bits and the oracle's: chunks per row that divide / do not divide the row, more chunks than
     resident warps, a grid smaller than one chunk; with and without the lean variant and culling."""
     import torch
     pos = scenes.wave_grid_pos(n)
@@ -1143,8 +1144,9 @@ def test_grid_tile_rasteriser_equals_gather_kernel(tina, O, n, W, H):
     fv = O.grid_faces(pos)
     for culling in (True, False):
         keys = []
-        for tuning in (dict(), dict(grid_tiles=1), dict(grid_tiles=1, lean_kernels=0), dict(grid_tiles=1, force_general=1),
-                       dict(grid_tiles=1, tiny_max=2), dict(lean_kernels=0), dict(tiny_max=2)):
+        for tuning in (dict(), dict(grid_quads=0), dict(grid_quads=0, lean_kernels=0), dict(force_general=1), dict(grid_tiles=1),
+                       dict(grid_tiles=1, lean_kernels=0), dict(grid_tiles=1, force_general=1), dict(grid_tiles=1, tiny_max=2),
+                       dict(lean_kernels=0), dict(tiny_max=2), dict(tiny_max=0), dict(grid_quads=0, tiny_max=2)):
             scene = tina.Scene((W, H), smoothing=True, culling=culling)
             grid = tina.MeshGrid(n)
             grid.pos.from_numpy(pos)
