@@ -13,7 +13,7 @@ Default workload C2 (BASELINE.json configs[1]): one "step" = one frame of the ho
                between steps, max over ranks
   e2e          the same metric through the public Python API with HOST buffers: pinned H2D of the frame's vertex
                grid, set_object, the step, pinned D2H of the image (3 frames in flight)
-  roofline     dominant kernel (k_raster_indexed): algorithmic bytes / CUDA-event duration vs MEASURED_PEAKS.json
+  roofline     dominant kernel (k_raster_quads): algorithmic bytes / CUDA-event duration vs MEASURED_PEAKS.json
   cpu_baseline the CPU oracle (port of the reference algorithm; the reference itself needs a Taichi 0.7 runtime
                that cannot be installed here) on this box's host cores
   extra        the two partitioned configs of BASELINE.json at this N: C4 (cornell.gltf, 64 views at 1024^2,
@@ -38,7 +38,7 @@ sys.path.insert(0, os.path.join(ROOT, 'tests'))
 
 import numpy as np  # noqa: E402
 
-K1_NCU = 'r2_v2_k_raster_indexed_ncu.txt'
+K1_NCU = 'r2_v3_k_raster_quads_ncu.txt'
 
 
 def ncu_traffic(kernel_file=K1_NCU):
@@ -618,10 +618,10 @@ def run_ours(args):
             'kernel_ms_mode': 'one CUDA-event pair per kernel, programmatic dependent launch off (the events would break the '
                               'launch pairing), adaptive tile-path skipping as in the timed steps; their sum exceeds ms_per_step by the '
                               'launch gaps PDL hides',
-            'roofline': {'bound': 'hbm', 'kernel': 'k_raster_indexed', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+            'roofline': {'bound': 'hbm', 'kernel': 'k_raster_quads' if w['kind'] == 'grid' else ('k_raster_indexed' if w['kind'] == 'monkey' else 'k_raster_faces'), 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                          'frac': achieved / peak, 'traffic': ncu_traffic() if wl == 'c2' else None,
                          'traffic_source': f'profiles/{K1_NCU} (ncu --set full, cold cache, dram read+write per launch)',
-                         'note': 'latency / occupancy-bound kernel: ncu smsp__issue_active 66 %, long-scoreboard 4.0 cycles per issue, DRAM 14 % of peak (same file)',
+                         'note': 'latency / occupancy-bound kernel: ncu smsp__issue_active 67 %, long-scoreboard 2.8 cycles per issue, DRAM 16 % of peak (same file)',
                          'alg_bytes': k1_bytes, 'peak_source': peak_src},
             'cpu_baseline': cpu,
             'e2e': {'value': e2e_value, 'unit': unit, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
@@ -631,7 +631,7 @@ def run_ours(args):
                     'note': 'floor = the f32 image over PCIe (d2h_only_ms, every rank copying at once)',
                     'cpus_bound_per_rank': env['ncpus']},
             # counted by the library (tina_launch_count) on rank 0, x ranks: k_frame_prologue (vertex records + the deferred
-            # key clear), k_raster_indexed, [k_large_path unless the adaptive tile path is skipping it], k_render_color per step
+            # key clear), k_raster_quads, [k_large_path unless the adaptive tile path is skipping it], k_render_color per step
             'gpu_launches': int(round(my_launches)) * world,
             'clocks': clocks,
             'extra': extra,
