@@ -596,7 +596,7 @@ k_render_color(const long long *__restrict__ keys, const float *__restrict__ ver
                const unsigned *__restrict__ counters, int pix_lo, int pix_hi, unsigned *__restrict__ pubstate,
                unsigned char flagval, const __grid_constant__ PeerTab peers, long long *__restrict__ keys_out,
                float *__restrict__ acc_rt, int acc_count) {
-    static_assert(K4_THREADS == (1 << FLAG_SHIFT), "one coverage flag per K4 block");
+    static_assert((1 << FLAG_SHIFT) % K4_THREADS == 0 && (K4_THREADS * 3) % 4 == 0, "a K4 block lies inside one coverage chunk");
     float *const acc = GLUE ? acc_rt : nullptr;
     pdl_wait();
     if (blockIdx.x == 0 && threadIdx.x == 0 && publish) { // tell the host how many faces needed the tile path
@@ -635,11 +635,10 @@ k_render_color(const long long *__restrict__ keys, const float *__restrict__ ver
     };
     // (CTAs take the chunks in plain order: spreading covered and background chunks over the launch -- CTA b -> chunk
     // (b % 8) * n / 8 + b / 8 -- measured 1.3 us slower on C2, profiles/r2_k4_variants.md)
-    const unsigned chunk = blockIdx.x;
-    const long long p0 = (long long)pix_lo + ((long long)chunk << FLAG_SHIFT);
+    const long long p0 = (long long)pix_lo + (long long)blockIdx.x * K4_THREADS;
     // flagval != 0: this object's render_occup was the engine's last, its flags carry its own stamp -> a chunk with
     // any other value holds none of its pixels.  flagval == 0: only "nothing rasterised here since the clear" is known.
-    const unsigned char cf = blkflags ? blkflags[(pix_lo >> FLAG_SHIFT) + chunk] : (unsigned char)1;
+    const unsigned char cf = blkflags ? blkflags[p0 >> FLAG_SHIFT] : (unsigned char)1;
     if (blkflags && (flagval ? cf != flagval : cf == 0)) {
         if (finish) {
             if (p0 + threadIdx.x < npix) finish_pixel(p0 + threadIdx.x);
@@ -652,8 +651,8 @@ k_render_color(const long long *__restrict__ keys, const float *__restrict__ ver
                     out[0] = r, out[1] = g, out[2] = b;
                     accumulate(p0 + t, r, g, b);
                 }
-            } else if (np == K4_THREADS && (((uintptr_t)image) & 15) == 0) { // 3072 contiguous, 16-byte aligned bytes: 192 float4 stores
-                if (t < 192) {
+            } else if (np == K4_THREADS && (((uintptr_t)image) & 15) == 0) { // K4_THREADS * 12 contiguous, 16-byte aligned bytes
+                if (t < K4_THREADS * 3 / 4) {
                     const int m = t % 3;
                     const float4 v = m == 0 ? make_float4(r, g, b, r) : m == 1 ? make_float4(g, b, r, g) : make_float4(b, r, g, b);
                     __stcs(reinterpret_cast<float4 *>(image + p0 * 3) + t, v);
