@@ -32,4 +32,5 @@ for rep in range(2):
         raster.set_tuning(profile=1); step(); torch.cuda.synchronize()
         kt = {k: round(x * 1e3, 1) for k, x in raster.kernel_times().items() if x > 0}
         raster.set_tuning(profile=0)
-        print(f'{knob}={v}: median {np.median(t):.1f} us  min {t.min():.1f} us  kernels(us) {kt}', flush=True)
+        ts_ = np.sort(t)[10:-10]
+        print(f'{knob}={v}: mean {t.mean():.2f} trimmed {ts_.mean():.2f} median {np.median(t):.1f} us  min {t.min():.1f} us  kernels(us) {kt}', flush=True)
