@@ -2,7 +2,7 @@
 """bench.py -- headline benchmark of the B200 triangle-raster hot path.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--workload c2|c1|c3|c4|c5] [--no-cpu] [--no-extra]
+                    [--workload c2|c2b|c1|c3|c4|c5] [--no-cpu] [--no-extra]
 
 Default workload C2 (BASELINE.json configs[1]): one "step" = one frame of the hot path on one GPU,
     Engine.clear_depth -> TriangleRaster.render_occup -> TriangleRaster.render_color
@@ -16,7 +16,8 @@ Default workload C2 (BASELINE.json configs[1]): one "step" = one frame of the ho
   roofline     dominant kernel (k_raster_quads): algorithmic bytes / CUDA-event duration vs MEASURED_PEAKS.json
   cpu_baseline the CPU oracle (port of the reference algorithm; the reference itself needs a Taichi 0.7 runtime
                that cannot be installed here) on this box's host cores
-  extra        the two partitioned configs of BASELINE.json at this N: C4 (cornell.gltf, 64 views at 1024^2,
+  extra        C2b (the grid wrapped in MeshNoCulling like the reference's own wave example) and the two partitioned
+               configs of BASELINE.json at this N: C4 (cornell.gltf, 64 views at 1024^2,
                view-partitioned, each rank's views replayed as one CUDA graph; strong scaling) and C5 (134 M-face
                soup at 7680x4320, sort-last by face range + key composite over NVLink; strong scaling), with the
                key / image checksums that must not depend on N
@@ -72,6 +73,9 @@ SOUP_S_C3, SOUP_S_C5 = 0.001374, 0.000487  # tests/scenes.py: calibrated with th
 WORKLOADS = {
     'c2': dict(kind='grid', n=1024, W=1920, H=1080, smoothing=True, material='classic', scaling='weak',
                desc='C2 MeshGrid(1024) wave t=0.25, 2093058 faces, 1920x1080, smooth normals, Classic (Lambert+Phong)'),
+    'c2b': dict(kind='grid', n=1024, W=1920, H=1080, smoothing=True, material='classic', scaling='weak', nocull=True,
+                desc='C2b MeshNoCulling(MeshGrid(1024)) wave t=0.25 (examples/meshgrid_wave.py:21), 4186116 faces, 1920x1080, '
+                     'smooth normals, Classic (Lambert+Phong)'),
     'c1': dict(kind='monkey', W=512, H=512, smoothing=False, material='diffuse', scaling='weak',
                desc='C1 monkey.obj 968 faces, 512x512, flat, Diffuse'),
     'c3': dict(kind='soup', nfaces=16 * 2**20, W=3840, H=2160, smoothing=False, material='diffuse', s=0.00105, scaling='weak',
@@ -103,7 +107,7 @@ def config_for(wl, world):
 def metric_for(wl):
     if wl == 'c4':
         return 'views/s (Scene.render, 64-view batch at 1024x1024)', 'views/s'
-    if wl == 'c2':
+    if wl in ('c2', 'c2b'):
         return 'Mtris/s (render_occup+render_color, 1080p)', 'Mtris/s'
     return 'Mtris/s (render_occup+render_color)', 'Mtris/s'
 
@@ -169,12 +173,14 @@ def cpu_inputs(wl):
     if w['kind'] == 'grid':
         pos = R.wave_grid_pos(w['n'])
         verts, norms = O.grid_faces(pos), O.grid_faces(O.grid_normals(pos))
+        if w.get('nocull'):
+            verts, norms, _ = O.no_culling(verts, norms)
     elif w['kind'] == 'monkey':
         verts, norms = R.monkey_faces(os.path.join(ROOT, 'tests', 'assets', 'monkey.obj')), None
     elif w['kind'] == 'soup':
         verts, norms = R.soup(w['nfaces'], w['W'], w['H'], s=w['s']), None
     else:
-        raise SystemExit(f'--impl reference / cpu_baseline is provided for c1, c2, c3 (not {wl})')
+        raise SystemExit(f'--impl reference / cpu_baseline is provided for c1, c2, c2b, c3 (not {wl})')
     return dict(verts=verts, norms=norms, view=view, proj=proj, nfaces=len(verts))
 
 
@@ -285,11 +291,21 @@ def make_env():
                 ncpus=ncpus)
 
 
-def timed_steps(env, step, K, warmup):
+def timed_steps(env, step, K, warmup, sweep=None):
     """W warm-up steps, then K steps with per-step CUDA events, L2 flushed between steps; -> (ms per step = sum of the
-    per-step times / K, max over ranks; per-step array of this rank; wall seconds of the timed region)."""
+    per-step times / K, max over ranks; per-step array of this rank; wall seconds of the timed region).
+    sweep: a second > L2 buffer that is READ after the flush write, so that the step starts on an L2 full of clean
+    foreign lines instead of dirty ones (informational figure; the headline uses the plain write flush)."""
     import torch
-    flush = env['flush']
+    fill = env['flush']
+
+    class _F:
+        @staticmethod
+        def fill_(v):
+            fill.fill_(v)
+            if sweep is not None:
+                sweep.amax()
+    flush = _F
     for _ in range(max(3, warmup)):
         step()
         flush.fill_(1.0)
@@ -402,6 +418,35 @@ def c5_measure(env, K, warmup, nfaces=None):
     return out
 
 
+def c2b_measure(env, K, warmup):
+    """C2b: the reference's own wave example wraps the grid in MeshNoCulling (examples/meshgrid_wave.py:21): twice the
+    faces, the generic indexed rasteriser (k_raster_indexed) instead of the quad kernel.  Same step, same timing."""
+    import scenes
+    import taichi_three_b200 as tina
+    w = WORKLOADS['c2b']
+    W, H = w['W'], w['H']
+    nfaces = 4 * (w['n'] - 1) ** 2
+    sc = tina.Scene((W, H), smoothing=True, maxfaces=nfaces, tonemap=False)
+    grid = tina.MeshGrid(w['n'])
+    grid.pos.from_numpy(scenes.wave_grid_pos(w['n'], t=0.25 + 0.01 * env['rank']))
+    ms, mt = tina.MeshNoCulling(grid), tina.Classic()
+    sc.add_object(ms, mt)
+    sc.engine.set_camera(*tina.orbit_camera(aspect=W / H))
+    raster, shader = sc.triangle_raster, sc.shaders[id(mt)]
+    raster.set_object(ms)
+    bg = np.zeros(3, np.float32)
+
+    def step():
+        sc.engine.clear_depth()
+        raster.render_occup()
+        raster.render_color(shader, fill_bg=bg)
+    ms_step, step_ms, _ = timed_steps(env, step, K, warmup)
+    frame_bytes, _ = alg_bytes('c2b', nfaces)
+    return dict(ms_per_step=ms_step, mtris_per_s=env['world'] * nfaces / ms_step / 1e3, faces=nfaces,
+                frame_roofline_frac=frame_bytes / (ms_step * 1e-3) / 1e9 / load_peaks()[0],
+                step_ms_min_median_max=[float(step_ms.min()), float(np.median(step_ms)), float(step_ms.max())])
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -446,7 +491,7 @@ def run_ours(args):
 
     # ---- C2 / C1 / C3: one frame per step on every rank ----
     if w['kind'] == 'grid':
-        inputs = dict(pos=scenes.wave_grid_pos(w['n'], t=0.25 + 0.01 * rank), nfaces=2 * (w['n'] - 1) ** 2)
+        inputs = dict(pos=scenes.wave_grid_pos(w['n'], t=0.25 + 0.01 * rank), nfaces=(4 if w.get('nocull') else 2) * (w['n'] - 1) ** 2)
     elif w['kind'] == 'monkey':
         obj = scenes.load_monkey()
         inputs = dict(obj=obj, nfaces=len(obj['f']))
@@ -461,6 +506,8 @@ def run_ours(args):
         if w['kind'] == 'grid':
             ms = tina.MeshGrid(w['n'])
             ms.pos.from_numpy(inputs['pos'])
+            if w.get('nocull'):
+                ms = tina.MeshNoCulling(ms)
         elif w['kind'] == 'monkey':
             ms = tina.MeshModel(inputs['obj'])
         else:
@@ -498,6 +545,12 @@ def run_ours(args):
         clocks['sampled'] = 'timed region + same workload looped to >= 0.6 s'
     value = world * nfaces / (ms_per_step * 1e-3) / 1e6
 
+    # ---- the same steps on a cold but CLEAN L2 (flush write followed by a 256 MiB read sweep), for information:
+    # after the write flush the step also pays the write-back of the flush buffer's dirty lines it evicts ----
+    sweep = torch.ones_like(flush)
+    clean_ms, _, _ = timed_steps(env, step, min(K, 100), 3, sweep=sweep)
+    del sweep
+
     # ---- back-to-back (no flush) for information ----
     barrier()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -527,7 +580,7 @@ def run_ours(args):
     def make_lane():
         sc, ms, sh = make_scene()
         if w['kind'] == 'grid':
-            src, dst = torch.as_tensor(inputs['pos']).pin_memory(), ms.pos.to_torch()
+            src, dst = torch.as_tensor(inputs['pos']).pin_memory(), (ms.mesh if w.get('nocull') else ms).pos.to_torch()
         elif w['kind'] == 'soup':
             src, dst = torch.as_tensor(inputs['tri']).pin_memory(), ms.verts.to_torch()
         else:
@@ -584,6 +637,11 @@ def run_ours(args):
         torch.cuda.empty_cache()
         extra = {}
         try:
+            extra['c2b'] = c2b_measure(env, 50, 5)
+        except Exception as ex:
+            extra['c2b'] = {'error': repr(ex)[:300]}
+        torch.cuda.empty_cache()
+        try:
             extra['c4'] = c4_measure(env, 10, 3)
         except Exception as ex:  # the headline line must survive a failure of the side measurements
             extra['c4'] = {'error': repr(ex)[:300]}
@@ -613,12 +671,13 @@ def run_ours(args):
             'frame_hbm_gbs': frame_bytes / (ms_per_step * 1e-3) / 1e9,
             'frame_roofline_frac': frame_bytes / (ms_per_step * 1e-3) / 1e9 / peak,
             'ms_per_step_back_to_back_no_flush': b2b_ms,
+            'ms_per_step_clean_cold_l2': clean_ms,
             'step_ms_min_median_max': [float(step_ms.min()), float(np.median(step_ms)), float(step_ms.max())],
             'kernel_ms': kmean,
             'kernel_ms_mode': 'one CUDA-event pair per kernel, programmatic dependent launch off (the events would break the '
                               'launch pairing), adaptive tile-path skipping as in the timed steps; their sum exceeds ms_per_step by the '
                               'launch gaps PDL hides',
-            'roofline': {'bound': 'hbm', 'kernel': 'k_raster_quads' if w['kind'] == 'grid' else ('k_raster_indexed' if w['kind'] == 'monkey' else 'k_raster_faces'), 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+            'roofline': {'bound': 'hbm', 'kernel': ('k_raster_indexed' if w.get('nocull') else 'k_raster_quads') if w['kind'] == 'grid' else ('k_raster_indexed' if w['kind'] == 'monkey' else 'k_raster_faces'), 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                          'frac': achieved / peak, 'traffic': ncu_traffic() if wl == 'c2' else None,
                          'traffic_source': f'profiles/{K1_NCU} (ncu --set full, cold cache, dram read+write per launch)',
                          'note': 'latency / occupancy-bound kernel: ncu smsp__issue_active 67 %, long-scoreboard 2.8 cycles per issue, DRAM 16 % of peak (same file)',
