@@ -322,6 +322,51 @@ int tina_image_tonemap(float *image, int64_t nfloats, void *stream);
 int tina_engine_ssao_render(TinaEngine *e, const float *normals, const float *samples, int nsamples, const float *rotations,
                             int noise_size, float radius, float thresh, float factor, float *ao, void *stream);
 int tina_image_ssao_apply(float *image, const float *ao, int W, int H, int noise_size, void *stream);
+/* SSAO with fresh samples per pixel and frame (postp/ssao.py:52-56, 80-81 `taa=True`): make_sample() draws three uniform
+ * numbers per sample.  The reference takes them from Taichi's global ti.random(), whose stream is not specified; here
+ * they come from the Wang hash of tina/random.py:26-35 seeded with (pixel, frame, draw index), so a frame is
+ * reproducible and the oracle restates it bit for bit.  apply_taa (:40-41): image *= 1 - ao. */
+int tina_engine_ssao_render_taa(TinaEngine *e, const float *normals, int nsamples, float radius, float thresh, float factor,
+                                uint32_t frame, float *ao, void *stream);
+int tina_image_ssao_apply_taa(float *image, const float *ao, int W, int H, void *stream);
+
+/* ---- SSR (postp/ssr.py) ------------------------------------------------------------------------------------------
+ * material.sample(idir, nrm, sign, rng) of matr/material.py as a tree the device walks: node 0 is the root; a node's
+ * parameters (MixMaterial / ScaleMaterial factor, Phong shineness, CookTorrance roughness + fresnel) are postfix value
+ * programs in code[] made of TINA_OP_CONST / INPUT / TEXTURE / FRESNEL (p0/n0 first parameter, p1/n1 second). */
+enum {
+    TINA_SNODE_LAMBERT = 0,  /* material.py:398-405 */
+    TINA_SNODE_PHONG = 1,    /* :459-472, p0 = shineness */
+    TINA_SNODE_COOK = 2,     /* :364-384, p0 = roughness, p1 = fresnel */
+    TINA_SNODE_EMISSION = 3, /* :679-681 */
+    TINA_SNODE_MIX = 4,      /* :123-138, a = mat1, b = mat2, p0 = factor */
+    TINA_SNODE_SCALE = 5,    /* :180-184, a = mat, p0 = factor */
+    TINA_SNODE_ADD = 6,      /* :227-238, a = mat1, b = mat2 */
+};
+#define TINA_SAMPLE_MAX_NODES 16
+#define TINA_SAMPLE_MAX_INSTR 48
+typedef struct {
+    int32_t kind, a, b, p0, n0, p1, n1, pad_;
+} TinaSampleNode;
+typedef struct {
+    int32_t nnodes, ncode, ntex, pad_;
+    const float *tex[TINA_MAX_TEX]; /* device, [w][h][c] f32 */
+    int32_t tex_w[TINA_MAX_TEX], tex_h[TINA_MAX_TEX], tex_c[TINA_MAX_TEX];
+    TinaSampleNode nodes[TINA_SAMPLE_MAX_NODES];
+    TinaInstr code[TINA_SAMPLE_MAX_INSTR];
+} TinaSampleMaterial;
+/* SSR.render (ssr.py:44-103): per pixel with a normal, nsamples reflection rays drawn with material.sample() of the
+ * pixel's material (table_host[mtlid[P]]) and marched through the engine's depth buffer for at most nsteps steps; a hit
+ * adds bilerp(image) * weight.  normals [W,H,3], coors [W,H,2] or NULL (the reference's dummy (1,1) field: texcoord 0),
+ * mtlid int32 [W,H], image [W,H,3] (read only), out4 [W,H,4].  Random numbers: taa = 0: WangHashRNG(P % blurring)
+ * exactly as ssr.py:73-76 (tina/random.py:17-62); taa = 1 (ssr.py:72, Taichi's unspecified ti.random()): the same
+ * hash seeded with (pixel, frame).  Reference defaults (:20-28): nsamples 32 / 12 (taa), nsteps 32 / 64, stepsize 2,
+ * tolerance 15, blurring 4.
+ * SSR.apply (:30-42): image = image * (1 - res.w) + res.xyz with res = out4 (taa) or its blurring x blurring box mean. */
+int tina_engine_ssr_render(TinaEngine *e, const float *normals, const float *coors, const int32_t *mtlid,
+                           const TinaSampleMaterial *table_host, int nmaterials, const float *image, int nsamples, int nsteps,
+                           float stepsize, float tolerance, int blurring, int taa, uint32_t frame, float *out4, void *stream);
+int tina_image_ssr_apply(float *image, const float *img4, int W, int H, int blurring, int taa, void *stream);
 /* FXAA (postp/fxaa.py:28-68) in place on image [W,H,3]; scratch_lumi [W*H], scratch_copy [W*H*3] floats.
  * Reference defaults: abs_thresh 0.0625, rel_thresh 0.063, factor 1.  Out-of-image taps read 0. */
 int tina_image_fxaa(float *image, int W, int H, float *scratch_lumi, float *scratch_copy, float abs_thresh,

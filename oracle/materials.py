@@ -220,3 +220,100 @@ def stock_classic(color=None, shineness=32, specular=0.4):
     def part(diff, spec):
         return [_c(specular), col] + diff + [_O(OP_MUL)] + spec + [_O(OP_MIX)]
     return _pod([part([_O(OP_LAMBERT)], [_c(shineness), _O(OP_PHONG)]), part([_c(1.0)], [_c(1.0)]), part([_c(0.0)], [_c(0.0)])])
+
+
+# ---- material.sample() trees for SSR (postp/ssr.py:78-80; matr/material.py sample methods) ------------------------
+(SN_LAMBERT, SN_PHONG, SN_COOK, SN_EMISSION, SN_MIX, SN_SCALE, SN_ADD) = range(7)
+SAMPLE_MAX_NODES, SAMPLE_MAX_INSTR = 16, 48
+
+
+class SampleNode(C.Structure):  # include/tina_b200.h: TinaSampleNode
+    _fields_ = [('kind', C.c_int32), ('a', C.c_int32), ('b', C.c_int32), ('p0', C.c_int32), ('n0', C.c_int32),
+                ('p1', C.c_int32), ('n1', C.c_int32), ('pad_', C.c_int32)]
+
+
+class SampleMaterialPOD(C.Structure):  # TinaSampleMaterial
+    _fields_ = [('nnodes', C.c_int32), ('ncode', C.c_int32), ('ntex', C.c_int32), ('pad_', C.c_int32),
+                ('tex', C.c_void_p * MAX_TEX), ('tex_w', C.c_int32 * MAX_TEX), ('tex_h', C.c_int32 * MAX_TEX),
+                ('tex_c', C.c_int32 * MAX_TEX), ('nodes', SampleNode * SAMPLE_MAX_NODES), ('code', Instr * SAMPLE_MAX_INSTR)]
+
+
+def _is_scalar(node):
+    """Does the reference evaluate this parameter node to a scalar (Vavg leaves it alone, common.py:36-40)?"""
+    k = _kind(node)
+    if k == 'Const':
+        return np.ndim(node.value) == 0 or np.size(node.value) == 1
+    if k == 'Param':
+        return np.ndim(node[None]) == 0
+    if k == 'Texture':
+        img = node.image if hasattr(node, 'image') else node.texture
+        shape = img.shape if hasattr(img, 'shape') else ()
+        return len(shape) == 2 or (len(shape) == 3 and shape[2] == 1)
+    if k == 'FresnelFactor':
+        return all(_is_scalar(_param(node, key)) for key in ('metallic', 'albedo', 'specular'))
+    return False  # Input: vectors
+
+
+def sample_pod_of(material):
+    """node graph -> (SampleMaterialPOD, host texture arrays): the tree material.sample() descends (node 0 = root)."""
+    P = _Prog()
+    nodes = []
+
+    def value(node):
+        start = len(P.code)
+        _value(P, node)
+        return start, len(P.code) - start
+
+    def walk(m):
+        k = _kind(m)
+        idx = len(nodes)
+        rec = dict(kind=0, a=0, b=0, p0=0, n0=0, p1=0, n1=0, pad_=0)
+        nodes.append(rec)
+        if k == 'MixMaterial':
+            f = _param(m, 'factor')
+            rec['kind'] = SN_MIX
+            rec['p0'], rec['n0'] = value(f)
+            rec['pad_'] = 1 if _is_scalar(f) else 0
+            rec['a'], rec['b'] = walk(m.mat1), walk(m.mat2)
+        elif k == 'ScaleMaterial':
+            rec['kind'] = SN_SCALE
+            rec['p0'], rec['n0'] = value(_param(m, 'factor'))
+            rec['a'] = walk(m.mat)
+        elif k == 'AddMaterial':
+            rec['kind'] = SN_ADD
+            rec['a'], rec['b'] = walk(m.mat1), walk(m.mat2)
+        elif k == 'Lambert':
+            rec['kind'] = SN_LAMBERT
+        elif k == 'Phong':
+            rec['kind'] = SN_PHONG
+            rec['p0'], rec['n0'] = value(_param(m, 'shineness'))
+        elif k == 'CookTorrance':
+            rec['kind'] = SN_COOK
+            rec['p0'], rec['n0'] = value(_param(m, 'roughness'))
+            rec['p1'], rec['n1'] = value(_param(m, 'fresnel'))
+        elif k == 'Emission':
+            rec['kind'] = SN_EMISSION
+        else:
+            raise NotImplementedError(k)
+        return idx
+
+    walk(material)
+    assert len(nodes) <= SAMPLE_MAX_NODES and len(P.code) <= SAMPLE_MAX_INSTR
+    pod = SampleMaterialPOD()
+    pod.nnodes, pod.ncode, pod.ntex = len(nodes), len(P.code), len(P.textures)
+    for i, rec in enumerate(nodes):
+        for key, v in rec.items():
+            setattr(pod.nodes[i], key, v)
+    for i, (op, arg, c) in enumerate(P.code):
+        pod.code[i].op, pod.code[i].arg = op, arg
+        pod.code[i].c[0], pod.code[i].c[1], pod.code[i].c[2] = c
+    arrays = []
+    for t in P.textures:
+        a = np.ascontiguousarray(t.to_numpy() if hasattr(t, 'to_numpy') else t, dtype=np.float32)
+        if a.ndim == 2:
+            a = a[:, :, None]
+        arrays.append(np.ascontiguousarray(a[:, :, :3] if a.shape[2] == 4 else a))
+    for i, a in enumerate(arrays):
+        pod.tex[i] = a.ctypes.data
+        pod.tex_w[i], pod.tex_h[i], pod.tex_c[i] = a.shape
+    return pod, arrays

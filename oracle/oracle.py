@@ -202,6 +202,55 @@ def ssao_apply(image, ao, noise_size=4):
     return out
 
 
+def ssao_render_taa(depth, normals, W2V, V2W, nsamples=64, radius=0.2, thresh=0.0, factor=1.0, frame=0, bias=(0.5, 0.5)):
+    """postp/ssao.py with taa=True: per-pixel, per-frame samples from the hash stream (include/tina_b200.h)."""
+    depth = np.ascontiguousarray(depth, dtype=np.int32)
+    W, H = depth.shape
+    nrm, w2v, v2w, b = _f(normals), _f(W2V), _f(V2W), _f(bias)
+    ao = np.zeros((W, H), dtype=np.float32)
+    lib().orc_ssao_render_taa(depth.ctypes.data_as(C.c_void_p), _p(nrm), _p(w2v), _p(v2w), _p(b), W, H, int(nsamples),
+                              C.c_float(radius), C.c_float(thresh), C.c_float(factor), C.c_uint32(frame), _p(ao))
+    return ao
+
+
+def ssao_apply_taa(image, ao):
+    out = np.ascontiguousarray(image, dtype=np.float32).copy()
+    a = _f(ao)
+    lib().orc_ssao_apply_taa(_p(out), _p(a), out.shape[0], out.shape[1])
+    return out
+
+
+def ssr_render(depth, normals, coors, mtlid, materials, image, W2V, V2W, nsamples=32, nsteps=32, stepsize=2.0, tolerance=15.0,
+               blurring=4, taa=False, frame=0, bias=(0.5, 0.5)):
+    """postp/ssr.py:44-103.  materials: list of material node graphs (the scene's material table, scene/raster.py:43-49),
+    flattened by the oracle's own front-end (oracle/materials.py).  -> img4 [W, H, 4]."""
+    from . import materials as OM
+    depth = np.ascontiguousarray(depth, dtype=np.int32)
+    W, H = depth.shape
+    pods = [OM.sample_pod_of(m) for m in materials]
+    table = (OM.SampleMaterialPOD * max(1, len(pods)))()
+    texhost = (C.c_void_p * (OM.MAX_TEX * max(1, len(pods))))()
+    for i, (pod, arrays) in enumerate(pods):
+        table[i] = pod
+        for t, a in enumerate(arrays):
+            texhost[i * OM.MAX_TEX + t] = a.ctypes.data
+    nrm, img, w2v, v2w, b = _f(normals), _f(image), _f(W2V), _f(V2W), _f(bias)
+    co = _f(coors) if coors is not None else None
+    mid = np.ascontiguousarray(mtlid, dtype=np.int32)
+    out = np.zeros((W, H, 4), dtype=np.float32)
+    lib().orc_ssr_render(depth.ctypes.data_as(C.c_void_p), _p(nrm), _p(co), mid.ctypes.data_as(C.c_void_p), table, texhost, len(pods),
+                         _p(img), _p(w2v), _p(v2w), _p(b), W, H, int(nsamples), int(nsteps), C.c_float(stepsize), C.c_float(tolerance),
+                         int(blurring), int(bool(taa)), C.c_uint32(frame), _p(out))
+    return out
+
+
+def ssr_apply(image, img4, blurring=4, taa=False):
+    out = np.ascontiguousarray(image, dtype=np.float32).copy()
+    a = _f(img4)
+    lib().orc_ssr_apply(_p(out), _p(a), out.shape[0], out.shape[1], int(blurring), int(bool(taa)))
+    return out
+
+
 def tonemap(image):
     out = np.ascontiguousarray(image, dtype=np.float32).copy()
     lib().orc_tonemap(_p(out), C.c_int64(out.size))

@@ -235,6 +235,54 @@ Vector.unit = Matrix.unit
 Vector.zero = Matrix.zero
 
 
+class U32:
+    """ti.u32 scalar (tina/random.py: Wang hash): arithmetic modulo 2^32 with ints, f32 arithmetic with floats
+    (Taichi promotes u32 (op) f32 to f32: the integer is first rounded to f32)."""
+    __array_priority__ = 2000
+
+    def __init__(self, v):
+        self.v = builtins.int(v) & 0xffffffff
+
+    @staticmethod
+    def _int(o):
+        if isinstance(o, U32):
+            return o.v
+        if isinstance(o, (builtins.int, np.integer, IntRef)) and not isinstance(o, builtins.bool):
+            return builtins.int(o) & 0xffffffff
+        return None
+
+    def _bin(self, o, fi, ff, rev=False):
+        i = U32._int(o)
+        if i is not None:
+            return U32(fi(i, self.v) if rev else fi(self.v, i))
+        a, b = F32(self.v), F32(o)
+        return F32(ff(b, a) if rev else ff(a, b))
+
+    def __xor__(self, o): return self._bin(o, lambda a, b: a ^ b, None)
+    def __rxor__(self, o): return self._bin(o, lambda a, b: a ^ b, None, True)
+    def __and__(self, o): return self._bin(o, lambda a, b: a & b, None)
+    def __rand__(self, o): return self._bin(o, lambda a, b: a & b, None, True)
+    def __or__(self, o): return self._bin(o, lambda a, b: a | b, None)
+    def __ror__(self, o): return self._bin(o, lambda a, b: a | b, None, True)
+    def __lshift__(self, o): return U32(self.v << builtins.int(o))
+    def __rshift__(self, o): return U32(self.v >> builtins.int(o))
+    def __add__(self, o): return self._bin(o, lambda a, b: a + b, lambda a, b: a + b)
+    def __radd__(self, o): return self._bin(o, lambda a, b: a + b, lambda a, b: a + b, True)
+    def __sub__(self, o): return self._bin(o, lambda a, b: a - b, lambda a, b: a - b)
+    def __mul__(self, o): return self._bin(o, lambda a, b: a * b, lambda a, b: a * b)
+    def __rmul__(self, o): return self._bin(o, lambda a, b: a * b, lambda a, b: a * b, True)
+    def __mod__(self, o): return self._bin(o, lambda a, b: a % b, None)
+    def __truediv__(self, o): return F32(F32(self.v) / F32(builtins.int(o) if U32._int(o) is not None else o))
+    def __eq__(self, o): return self.v == (U32._int(o) if U32._int(o) is not None else o)
+    def __ne__(self, o): return not self.__eq__(o)
+    def __lt__(self, o): return self.v < (U32._int(o) if U32._int(o) is not None else o)
+    def __hash__(self): return hash(self.v)
+    def __int__(self): return self.v
+    def __index__(self): return self.v
+    def __float__(self): return builtins.float(self.v)
+    def __repr__(self): return f'U32({self.v})'
+
+
 def _scalar(x):
     x = np.asarray(x)
     if x.dtype == np.float64:
@@ -461,7 +509,14 @@ def make_taichi():
     ti.sqrt, ti.floor, ti.ceil = _unary(np.sqrt), _unary(np.floor), _unary(np.ceil)
     ti.sin, ti.cos, ti.exp, ti.log, ti.tan = _unary(np.sin), _unary(np.cos), _unary(np.exp), _unary(np.log), _unary(np.tan)
     ti.min, ti.max, ti.abs = shim_min, shim_max, shim_abs
-    ti.cast = lambda x, dt: _to_float(x) if _dtype(dt) == F32 else _to_int(x)
+    ti.u32 = 'u32'
+
+    def cast(x, dt):
+        if dt == 'u32':  # tina/random.py:29,48: scalars become U32; an integer vector keeps its (non-negative) i32 entries,
+            return x if isinstance(x, Matrix) else U32(x)  # which meet U32 operands through the reflected operators
+        return _to_float(x) if _dtype(dt) == F32 else _to_int(x)
+    ti.cast = cast
+    ti.expr_init = lambda x: x
 
     def atomic_min(ref, v):
         old = builtins.int(ref)
@@ -492,7 +547,7 @@ def make_transformations():
 
 NEEDED = ['common', 'advans', 'util.matrix', 'matr.nodes', 'matr.material', 'core.engine', 'core.lighting',
           'core.shader', 'core.triangle', 'mesh.base', 'mesh.simple', 'mesh.model', 'mesh.grid', 'mesh.trans',
-          'mesh.cull', 'mesh.norm', 'postp.tonemap', 'postp.fxaa', 'postp.blooming', 'postp.ssao', 'assimp.obj', 'assimp.gltf', 'core.particle', 'core.wireframe', 'mesh.wire', 'pars.base',
+          'mesh.cull', 'mesh.norm', 'postp.tonemap', 'postp.fxaa', 'postp.blooming', 'postp.ssao', 'random', 'postp.ssr', 'assimp.obj', 'assimp.gltf', 'core.particle', 'core.wireframe', 'mesh.wire', 'pars.base',
           'pars.simple', 'pars.trans', 'scene.raster']
 
 

@@ -847,6 +847,343 @@ void orc_ssao_apply(float *image, const float *ao, int W, int H, int noise) {
         }
 }
 
+/* ---- SSR (postp/ssr.py) and the random streams it draws from (tina/random.py) ------------------------------------ */
+
+/* random.py:26-35 WangHashRNG._noise */
+static uint32_t wang(uint32_t v) {
+    v = (v ^ 61u) ^ (v >> 16);
+    v *= 9u;
+    v ^= v << 4;
+    v *= 0x27d4eb2du;
+    v ^= v >> 15;
+    return v;
+}
+typedef struct {
+    uint32_t seed;
+} WangRNG;
+/* random.py:54-58: noise(seed) = (noise_int(seed) >> 1) * (2 / 4294967296) -- u32 -> f32 (rounded), times 2^-31; seed += 1 */
+static float rng_random(WangRNG *r) {
+    const uint32_t u = wang(r->seed) >> 1;
+    r->seed += 1u;
+    return (float)u * 4.656612873077393e-10f;
+}
+static uint32_t rng_random_int(WangRNG *r) { /* random.py:60-64 */
+    const uint32_t u = wang(r->seed);
+    r->seed += 1u;
+    return u;
+}
+
+/* a parameter program of a TinaSampleMaterial: TINA_OP_CONST / INPUT / TEXTURE / FRESNEL only (matr/nodes.py, material.py:69-83) */
+static void run_value(const TinaSampleMaterial *m, const float *const *texhost, int begin, int n, const ShadeInputs *in, float *out) {
+    float st[STK][3];
+    int sp = 0;
+    for (int pc = begin; pc < begin + n; pc++) {
+        const TinaInstr *I = &m->code[pc];
+        switch (I->op) {
+        case TINA_OP_CONST:
+            for (int k = 0; k < 3; k++) st[sp][k] = I->c[k];
+            sp++;
+            break;
+        case TINA_OP_INPUT: {
+            const float *src = I->arg == 0 ? in->pos : I->arg == 1 ? in->color : I->arg == 2 ? in->normal : in->texcoord;
+            for (int k = 0; k < 3; k++) st[sp][k] = src[k];
+            sp++;
+            break;
+        }
+        case TINA_OP_TEXTURE: {
+            float uv[2] = {st[sp - 1][0], st[sp - 1][1]};
+            tex_sample(texhost[I->arg], m->tex_w[I->arg], m->tex_h[I->arg], m->tex_c[I->arg], uv, st[sp - 1]);
+            break;
+        }
+        case TINA_OP_FRESNEL: {
+            float *specular = st[sp - 1], *albedo = st[sp - 2], *metallic = st[sp - 3];
+            for (int k = 0; k < 3; k++)
+                metallic[k] = metallic[k] * albedo[k] + (1.0f - metallic[k]) * 0.16f * (specular[k] * specular[k]);
+            sp -= 2;
+            break;
+        }
+        }
+    }
+    for (int k = 0; k < 3; k++) out[k] = sp > 0 ? st[sp - 1][k] : 0.0f;
+}
+
+/* advans.py:97-100 tangentspace(n) @ advans.py:105-108 spherical(h, p) */
+static void tangent_spherical(const float *n, float h, float p, float *o) {
+    const float up[3] = {233.0f, 666.0f, 512.0f};
+    float bitan[3], tan[3];
+    cross3(n, up, bitan);
+    normalize3(bitan);
+    cross3(bitan, n, tan);
+    const float ang = p * 6.283185307179586f;
+    const float s = sqrtf(fmaxf(0.0f, 1.0f - h * h));
+    const float ux = s * cosf(ang), uy = s * sinf(ang);
+    for (int k = 0; k < 3; k++) o[k] = (tan[k] * ux + bitan[k] * uy) + n[k] * h;
+}
+static void reflect_neg(const float *idir, const float *nrm, float *r) { /* common.py:198-199 reflect(-idir, nrm) */
+    const float I3[3] = {-idir[0], -idir[1], -idir[2]};
+    const float t = 2.0f * dot3(nrm, I3);
+    for (int k = 0; k < 3; k++) r[k] = I3[k] - t * nrm[k];
+}
+
+/* material.sample(idir, nrm, 1, rng) (matr/material.py) for the sub-tree rooted at `node`: -> odir, wei (rough is unused by SSR) */
+static void sample_node(const TinaSampleMaterial *m, const float *const *texhost, int node, const ShadeInputs *in,
+                        const float *idir, const float *nrm, WangRNG *rng, float *odir, float *wei) {
+    const TinaSampleNode *N = &m->nodes[node];
+    float p0[3] = {0, 0, 0}, p1[3] = {0, 0, 0};
+    if (N->n0) run_value(m, texhost, N->p0, N->n0, in, p0);
+    if (N->n1) run_value(m, texhost, N->p1, N->n1, in, p1);
+    switch (N->kind) {
+    case TINA_SNODE_LAMBERT: { /* material.py:398-405 */
+        float u = rng_random(rng);
+        const float v = rng_random(rng);
+        u = sqrtf(u);
+        tangent_spherical(nrm, u, v, odir);
+        normalize3(odir);
+        wei[0] = wei[1] = wei[2] = 1.0f;
+        break;
+    }
+    case TINA_SNODE_PHONG: { /* :459-472; the shineness is a scalar there */
+        const float mm = p0[0];
+        float u = rng_random(rng);
+        const float v = rng_random(rng);
+        u = powf(u, 1.0f / (mm + 1.0f));
+        float rdir[3];
+        reflect_neg(idir, nrm, rdir);
+        tangent_spherical(rdir, u, v, odir);
+        float w = 1.0f;
+        if (dot3(odir, nrm) < 0.0f) {
+            for (int k = 0; k < 3; k++) odir[k] = -odir[k];
+            w = 0.0f;
+        }
+        wei[0] = wei[1] = wei[2] = w;
+        break;
+    }
+    case TINA_SNODE_COOK: { /* :364-384 sample, :323-357 sub_brdf */
+        const float EPS = 1e-10f, eps = 1e-6f;
+        const float alpha2s = fmaxf(0.0f, p0[0] * p0[0]);
+        float u = rng_random(rng);
+        const float v = rng_random(rng);
+        u = sqrtf((1.0f - u) / (1.0f - u * (1.0f - alpha2s)));
+        float rdir[3];
+        reflect_neg(idir, nrm, rdir);
+        tangent_spherical(rdir, u, v, odir);
+        float half[3] = {idir[0] + odir[0], idir[1] + odir[1], idir[2] + odir[2]};
+        normalize3(half);
+        const float NoL = fmaxf(EPS, dot3(idir, nrm));
+        const float NoV = fmaxf(EPS, dot3(odir, nrm));
+        const float VoH = fminf((float)(1 - 1e-10), fmaxf(EPS, dot3(half, odir)));
+        const int flip = dot3(odir, nrm) < 0.0f;
+        for (int k = 0; k < 3; k++) {
+            const float alpha2 = fmaxf(eps, p0[k] * p0[k]);
+            const float kk = alpha2 / 2.0f;
+            float vdf = 1.0f / ((NoV * kk + 1.0f) - kk);
+            vdf *= 1.0f / ((NoL * kk + 1.0f) - kk);
+            vdf /= 1.0f * (1.0f - alpha2) + 12.566370614359172f * alpha2;
+            float fdf = p1[k] + (1.0f - p1[k]) * powf(1.0f - VoH, 5.0f);
+            if (flip) fdf = 0.0f;
+            wei[k] = fdf * vdf;
+        }
+        if (flip)
+            for (int k = 0; k < 3; k++) odir[k] = -odir[k];
+        break;
+    }
+    case TINA_SNODE_EMISSION: /* :679-681 */
+        for (int k = 0; k < 3; k++) odir[k] = idir[k], wei[k] = 0.0f;
+        break;
+    case TINA_SNODE_MIX: { /* :123-138 */
+        /* Vavg (common.py:36-40): a vector parameter is averaged, a scalar one is taken as it is (pad_ bit 0) */
+        float avg = (N->pad_ & 1) ? p0[0] : ((p0[0] + p0[1]) + p0[2]) / 3.0f;
+        float factor = avg; /* common.py:227-231 smoothlerp(avg, 0.12, 0.88) */
+        if (factor != 0.0f && factor != 1.0f) {
+            const float t = clamp01((factor - 0.0f) / (1.0f - 0.0f));
+            factor = t * t * (3.0f - 2.0f * t);
+            factor = 0.12f * (1.0f - factor) + 0.88f * factor;
+        }
+        if (rng_random(rng) < factor) {
+            sample_node(m, texhost, N->b, in, idir, nrm, rng, odir, wei);
+            for (int k = 0; k < 3; k++) wei[k] *= p0[k] / factor;
+        } else {
+            sample_node(m, texhost, N->a, in, idir, nrm, rng, odir, wei);
+            for (int k = 0; k < 3; k++) wei[k] *= (1.0f - p0[k]) / (1.0f - factor);
+        }
+        break;
+    }
+    case TINA_SNODE_SCALE: /* :180-184 */
+        sample_node(m, texhost, N->a, in, idir, nrm, rng, odir, wei);
+        for (int k = 0; k < 3; k++) wei[k] = wei[k] * p0[k];
+        break;
+    case TINA_SNODE_ADD: /* :227-238 */
+        sample_node(m, texhost, (rng_random_int(rng) % 2u == 0u) ? N->a : N->b, in, idir, nrm, rng, odir, wei);
+        for (int k = 0; k < 3; k++) wei[k] *= 2.0f;
+        break;
+    }
+}
+
+/* postp/ssr.py:44-103 render / render_at.  depth int32 [W][H], normals [W][H][3], coors [W][H][2] or NULL, mtlid int32
+ * [W][H], image [W][H][3]; out4 [W][H][4].  texhost[i] = host texture pointers of table[i] (TINA_MAX_TEX each).
+ * taa = 0: rng = WangHashRNG(P % blurring) (:73-76); taa = 1: the same hash seeded with (P.x, P.y, frame) (the
+ * reference's ti.random() stream is unspecified, include/tina_b200.h). */
+void orc_ssr_render(const int32_t *depth, const float *normals, const float *coors, const int32_t *mtlid,
+                    const TinaSampleMaterial *table, const float *const *texhost, int nmaterials, const float *image,
+                    const float *W2V, const float *V2W, const float *bias, int W, int H, int nsamples, int nsteps,
+                    float stepsize, float tolerance, int blurring, int taa, uint32_t frame, float *out4) {
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int i = 0; i < W; i++)
+        for (int j = 0; j < H; j++) {
+            const int64_t P = (int64_t)i * H + j;
+            float *o = out4 + P * 4;
+            const float *normal = normals + P * 3;
+            o[0] = o[1] = o[2] = o[3] = 0.0f;
+            if ((normal[0] * normal[0] + normal[1] * normal[1]) + normal[2] * normal[2] < 1e-6f) continue; /* :47-48 */
+            const int mid = mtlid[P];
+            if (mid < 0 || mid >= nmaterials) continue; /* (VirtualMaterial: no branch taken -> zeros) */
+            const TinaSampleMaterial *m = table + mid;
+            const float *const *th = texhost + (int64_t)mid * TINA_MAX_TEX;
+            const float p[2] = {(float)i + bias[0], (float)j + bias[1]};
+            const float vpos[3] = {p[0] / (float)W * 2.0f - 1.0f, p[1] / (float)H * 2.0f - 1.0f, (float)depth[P] / MAXDEPTH_F};
+            float pos[3];
+            mapply_pos(V2W, vpos, pos);
+            float q[3] = {vpos[0], vpos[1], -1.0f}, r0[3], r1[3], rd[3]; /* shader.py:82-93 calc_viewdir */
+            mapply_pos(V2W, q, r0);
+            q[2] = 1.0f;
+            mapply_pos(V2W, q, r1);
+            for (int k = 0; k < 3; k++) rd[k] = r1[k] - r0[k];
+            normalize3(rd);
+            const float viewdir[3] = {-rd[0], -rd[1], -rd[2]};
+            ShadeInputs in;
+            for (int k = 0; k < 3; k++) in.pos[k] = pos[k], in.color[k] = 1.0f, in.normal[k] = normal[k];
+            in.texcoord[0] = coors ? coors[P * 2] : 0.0f, in.texcoord[1] = coors ? coors[P * 2 + 1] : 0.0f, in.texcoord[2] = 0.0f;
+            WangRNG rng;
+            if (!taa) rng.seed = wang((uint32_t)(j % blurring) ^ wang((uint32_t)(i % blurring))); /* random.py:44-52 on P % blurring */
+            else rng.seed = wang(frame ^ wang((uint32_t)j ^ wang((uint32_t)i)));
+            float res[4] = {0, 0, 0, 0};
+            for (int s = 0; s < nsamples; s++) {
+                float odir[3], wei[3];
+                sample_node(m, th, 0, &in, viewdir, normal, &rng, odir, wei);
+                const float ov = dot3(odir, viewdir);
+                const float step = stepsize / (sqrtf(1.0f - ov * ov) * (float)nsteps);
+                float t3[3], v0[3], v1[3];
+                for (int k = 0; k < 3; k++) t3[k] = pos[k] - viewdir[k] / (float)nsteps;
+                mapply_pos(W2V, t3, v0);
+                mapply_pos(W2V, pos, v1);
+                const float vtol = tolerance * (v0[2] - v1[2]);
+                const float rr = rng_random(&rng);
+                float ro[3];
+                for (int k = 0; k < 3; k++) ro[k] = pos[k] + odir[k] * rr * step;
+                for (int t = 0; t < nsteps; t++) {
+                    float vro[3];
+                    for (int k = 0; k < 3; k++) ro[k] += odir[k] * step;
+                    mapply_pos(W2V, ro, vro);
+                    if (!(-1.0f <= vro[0] && vro[0] <= 1.0f && -1.0f <= vro[1] && vro[1] <= 1.0f && -1.0f <= vro[2] && vro[2] <= 1.0f)) break;
+                    const float Dx = (vro[0] * 0.5f + 0.5f) * (float)W, Dy = (vro[1] * 0.5f + 0.5f) * (float)H;
+                    const int ix = f2i(Dx), iy = f2i(Dy);
+                    const float d = (ix < 0 || iy < 0 || ix >= W || iy >= H) ? 0.0f : (float)depth[(int64_t)ix * H + iy] / MAXDEPTH_F;
+                    if (vro[2] - vtol < d && d < vro[2]) {
+                        float clr[3];
+                        bilerp3(image, W, H, Dx, Dy, clr);
+                        for (int k = 0; k < 3; k++) res[k] += clr[k] * wei[k];
+                        res[3] += 1.0f;
+                        break;
+                    }
+                }
+            }
+            for (int k = 0; k < 4; k++) o[k] = res[k] / (float)nsamples;
+        }
+}
+
+/* postp/ssr.py:30-42 apply: res = img4 (taa) or its blurring x blurring box mean (reads outside the field are 0);
+ * image = image * (1 - res.w) + res.xyz */
+void orc_ssr_apply(float *image, const float *img4, int W, int H, int blurring, int taa) {
+    const int offs = blurring / 2;
+    for (int i = 0; i < W; i++)
+        for (int j = 0; j < H; j++) {
+            float res[4] = {0, 0, 0, 0};
+            if (taa) {
+                memcpy(res, img4 + ((int64_t)i * H + j) * 4, sizeof res);
+            } else {
+                for (int k = 0; k < blurring; k++)
+                    for (int l = 0; l < blurring; l++) {
+                        const int x = i + k - offs, y = j + l - offs;
+                        if (x < 0 || y < 0 || x >= W || y >= H) continue;
+                        for (int c = 0; c < 4; c++) res[c] += img4[((int64_t)x * H + y) * 4 + c];
+                    }
+                for (int c = 0; c < 4; c++) res[c] /= (float)(blurring * blurring);
+            }
+            float *px = image + ((int64_t)i * H + j) * 3;
+            for (int c = 0; c < 3; c++) {
+                px[c] *= 1.0f - res[3];
+                px[c] += res[c];
+            }
+        }
+}
+
+/* postp/ssao.py:52-56,65-96 with taa=True: make_sample() per sample from the hash stream seeded with (P.x, P.y, frame)
+ * (include/tina_b200.h: tina_engine_ssao_render_taa) instead of the rotated table */
+void orc_ssao_render_taa(const int32_t *depth, const float *normals, const float *W2V, const float *V2W, const float *bias,
+                         int W, int H, int nsamples, float radius, float thresh, float factor, uint32_t frame, float *ao) {
+    for (int i = 0; i < W; i++)
+        for (int j = 0; j < H; j++) {
+            const int64_t P = (int64_t)i * H + j;
+            const float *normal = normals + P * 3;
+            const float p[2] = {(float)i + bias[0], (float)j + bias[1]};
+            float vpos[3] = {p[0] / (float)W * 2.0f - 1.0f, p[1] / (float)H * 2.0f - 1.0f, (float)depth[P] / MAXDEPTH_F};
+            float pos[3];
+            mapply_pos(V2W, vpos, pos);
+            float q[3] = {vpos[0], vpos[1], -1.0f}, ro[3], ro1[3], rd[3];
+            mapply_pos(V2W, q, ro);
+            q[2] = 1.0f;
+            mapply_pos(V2W, q, ro1);
+            for (int k = 0; k < 3; k++) rd[k] = ro1[k] - ro[k];
+            normalize3(rd);
+            const float viewdir[3] = {-rd[0], -rd[1], -rd[2]};
+            float t3[3], tv[3];
+            for (int k = 0; k < 3; k++) t3[k] = pos[k] - radius * viewdir[k];
+            mapply_pos(W2V, t3, tv);
+            const float vradius = tv[2] - vpos[2];
+            WangRNG rng;
+            rng.seed = wang(frame ^ wang((uint32_t)j ^ wang((uint32_t)i)));
+            float occ = 0.0f;
+            for (int s = 0; s < nsamples; s++) {
+                /* ssao.py:52-56 make_sample: u, v = random(), random(); r = lerp(random() ** 1.5, .01, 1); u = lerp(u, .01, 1) */
+                float u = rng_random(&rng);
+                const float v = rng_random(&rng);
+                const float w = powf(rng_random(&rng), 1.5f);
+                const float r = 0.01f * (1.0f - w) + 1.0f * w;
+                u = 0.01f * (1.0f - u) + 1.0f * u;
+                float dir[3], sp[3], sv[3];
+                { /* tangentspace(normal) @ (spherical(u, v) * r): the sample is scaled before the basis change */
+                    const float up[3] = {233.0f, 666.0f, 512.0f};
+                    float bitan[3], tan[3];
+                    cross3(normal, up, bitan);
+                    normalize3(bitan);
+                    cross3(bitan, normal, tan);
+                    const float ang = v * 6.283185307179586f, sq = sqrtf(fmaxf(0.0f, 1.0f - u * u));
+                    const float sx = sq * cosf(ang) * r, sy = sq * sinf(ang) * r, sz = u * r;
+                    for (int k = 0; k < 3; k++) dir[k] = (tan[k] * sx + bitan[k] * sy) + normal[k] * sz;
+                }
+                for (int k = 0; k < 3; k++) sp[k] = pos[k] + dir[k] * radius;
+                mapply_pos(W2V, sp, sv);
+                const float Dx = (sv[0] * 0.5f + 0.5f) * (float)W, Dy = (sv[1] * 0.5f + 0.5f) * (float)H;
+                if (0.0f <= Dx && Dx < (float)W && 0.0f <= Dy && Dy < (float)H) {
+                    const float d = (float)depth[(int64_t)f2i(Dx) * H + f2i(Dy)] / MAXDEPTH_F;
+                    if (d < sv[2]) {
+                        float rc = vradius / (vpos[2] - d);
+                        const float t = clamp01((fabsf(rc) - 0.0f) / (1.0f - 0.0f));
+                        occ += t * t * (3.0f - 2.0f * t);
+                    }
+                }
+            }
+            float a = occ / (float)nsamples;
+            a = factor * (a - thresh);
+            ao[P] = clamp01(a);
+        }
+}
+
+void orc_ssao_apply_taa(float *image, const float *ao, int W, int H) { /* ssao.py:40-41: out *= 1 - img */
+    for (int64_t P = 0; P < (int64_t)W * H; P++)
+        for (int c = 0; c < 3; c++) image[P * 3 + c] *= 1.0f - ao[P];
+}
+
 void orc_grid_normals(const float *pos, int nx, int ny, float *nrm) {
     for (int i = 0; i < nx; i++)
         for (int j = 0; j < ny; j++) {

@@ -354,6 +354,64 @@ def case_ssao():
     print('particles_ssao: ao mean %.4f max %.4f, %d B' % (out['ao'].mean(), out['ao'].max(), os.path.getsize(path)))
 
 
+def case_ssr():
+    """postp/ssr.py inside Scene(ssr=True, texturing=True) (scene/raster.py:43-64,192-194): three objects with different
+    material graphs (a textured PBR, Classic, an Add / Scale / Mix / Emission composite with a vector mix factor), the
+    normal / texcoord / material-id G-buffers, the SSR field (non-TAA: WangHashRNG(P % blurring), ssr.py:73-76) and the
+    image before / after SSR.apply.  The material table is filled by hand after add_object: the reference does that in a
+    materialize callback, which real Taichi runs at the first kernel launch and the shim at construction.
+    nsamples 6 / nsteps 16 instead of 32 / 32 keep the serial Python run short (the fields are public, ssr.py:8-12)."""
+    rng = np.random.default_rng(20241018)
+    tex0 = rng.random((6, 5, 3)).astype(np.float32)
+    ns = {n: getattr(tina, n) for n in ('PBR', 'Classic', 'Diffuse', 'Lamp', 'Lambert', 'Phong', 'Emission', 'CookTorrance', 'Texture',
+                                        'FresnelFactor', 'MixMaterial', 'ScaleMaterial', 'AddMaterial')}
+    ns.update(tex0=tex0)
+    specs = ['PBR(basecolor=Texture(tex0), metallic=0.7, roughness=0.15)',
+             'Classic(color=[0.9, 0.85, 0.6], shineness=24, specular=0.5)',
+             'MixMaterial(AddMaterial(ScaleMaterial(Lambert(), [0.2, 0.5, 0.8]), ScaleMaterial(Emission(), 0.3)), '
+             'CookTorrance(roughness=0.3, fresnel=[0.9, 0.6, 0.4]), [0.3, 0.5, 0.7])']
+    W, H = 48, 40
+    scene = tina.Scene((W, H), smoothing=True, texturing=True, ssr=True, tonemap=False)
+    mats = [eval(sp, dict(ns)) for sp in specs]
+    scene.add_object(tina.MeshModel(os.path.join(REF, 'assets/monkey.obj')), mats[0])
+    floor = tina.MeshTransform(tina.MeshModel(os.path.join(REF, 'assets/plane.obj')), tina.translate([0, -0.9, 0]) @ tina.scale(2.5))
+    scene.add_object(floor, mats[1])
+    ball = tina.MeshTransform(tina.MeshModel(os.path.join(REF, 'assets/sphere.obj')), tina.translate([1.3, -0.3, 0.2]) @ tina.scale(0.55))
+    scene.add_object(ball, mats[2])
+    camera(scene, W / H, back=(0.3, 0.8, 3.0))
+    scene.mtltab.clear_materials()
+    for m in scene.materials:
+        scene.mtltab.add_material(m)
+    scene.ssr.nsamples[None], scene.ssr.nsteps[None] = 6, 16
+    eng = scene.engine
+    scene.image.fill(scene.bgcolor)
+    eng.clear_depth()
+    for sh in scene.pre_shaders + scene.post_shaders:
+        sh.clear_buffer()
+    for obj, oinfo in scene.objects.items():
+        oinfo.raster.set_object(obj)
+        oinfo.raster.render_occup()
+        oinfo.raster.render_color(scene.shaders[oinfo.material])
+    out = {'W2V': eng.W2V.to_numpy().astype(np.float32), 'V2W': eng.V2W.to_numpy().astype(np.float32),
+           'depth': eng.depth.to_numpy().astype(np.int32), 'normals': scene.norm_buffer.to_numpy().astype(np.float32),
+           'coors': scene.coor_buffer.to_numpy().astype(np.float32), 'mtlid': scene.mtlid_buffer.to_numpy().astype(np.int32),
+           'image_before': scene.image.to_numpy().astype(np.float32), 'tex0': tex0, 'nspecs': np.int32(len(specs)),
+           'nsamples': np.int32(6), 'nsteps': np.int32(16), 'stepsize': np.float32(scene.ssr.stepsize[None]),
+           'tolerance': np.float32(scene.ssr.tolerance[None]), 'blurring': np.int32(scene.ssr.blurring[None])}
+    for i, sp in enumerate(specs):
+        out[f'spec{i}'] = np.array(sp)
+    scene.ssr.render(eng, scene.image)
+    out['ssr'] = scene.ssr.img.to_numpy().astype(np.float32)
+    scene.ssr.apply(scene.image)
+    out['image_after'] = scene.image.to_numpy().astype(np.float32)
+    path = os.path.join(HERE, 'particles_ssr.npz')  # (particles_ prefix = not a plain raster scene, see test_golden.CASES)
+    np.savez_compressed(path, **out)
+    hit = out['ssr'][..., 3] > 0
+    print('particles_ssr: %d px with a normal, %d with hits, mean alpha %.4f, materials hit %s, %d B' % (
+        int((np.square(out['normals']).sum(-1) >= 1e-6).sum()), int(hit.sum()), float(out['ssr'][..., 3].mean()),
+        sorted(set(out['mtlid'][hit].tolist())), os.path.getsize(path)))
+
+
 def case_micro():
     """The C2 regime at golden size: sub-pixel faces.  (a) MeshGrid(56) wave on a 40x30 screen (~0.3 px per face,
     smooth normals, Classic) -- most faces cover no sample, many samples lie within 1e-2 px of an edge;
@@ -481,6 +539,7 @@ if __name__ == '__main__':
         sys.exit(0)
     case_micro()
     case_ssao()
+    case_ssr()
     case_monkey()
     case_grid()
     case_cornell()

@@ -235,6 +235,20 @@ def test_oracle_postfx_match_reference_sources(tina, O):
     assert np.abs(O.bloom(g['input'], gw) - g['bloom']).max() <= 1e-6
 
 
+def test_oracle_ssr_matches_reference_sources(tina, O):
+    """postp/ssr.py run from the reference's own sources under the shim (golden: depth, normal / texcoord / material-id
+    G-buffers, three material graphs incl. a textured PBR and an Add / Scale / Mix / Emission composite): the oracle's
+    material.sample() trees, Wang-hash stream and ray march reproduce the SSR field, SSR.apply is bit-exact."""
+    g = np.load(os.path.join(GOLDEN, 'particles_ssr.npz'))
+    mats = [_material(tina, g, i, 'spec') for i in range(int(g['nspecs']))]
+    img4 = O.ssr_render(g['depth'], g['normals'], g['coors'], g['mtlid'], mats, g['image_before'], g['W2V'], g['V2W'],
+                        nsamples=int(g['nsamples']), nsteps=int(g['nsteps']), stepsize=float(g['stepsize']),
+                        tolerance=float(g['tolerance']), blurring=int(g['blurring']))
+    assert (g['ssr'][..., 3] > 0).sum() > 300
+    assert np.abs(img4 - g['ssr']).max() <= 2e-6
+    assert np.array_equal(O.ssr_apply(g['image_before'], g['ssr'], int(g['blurring'])), g['image_after'])
+
+
 def test_oracle_ssao_matches_reference_sources(tina, O):
     """postp/ssao.py run from the reference's own sources under the shim (golden: depth, normal G-buffer, the sample /
     rotation tables it drew, the AO field, the image before and after apply) against the oracle restatement."""
