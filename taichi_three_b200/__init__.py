@@ -19,7 +19,7 @@ from .engine import Engine
 from .triangle import TriangleRaster
 from .particle import ParticleRaster, SimpleParticles, ParsTransform
 from .wireframe import WireframeRaster, MeshToWire
-from .postp import FXAA, Blooming, SSAO
+from .postp import FXAA, Blooming, SSAO, SSR
 from .scene import Scene
 from .control import Control, RotationStep
 from .field import Field

@@ -43,6 +43,22 @@ class TinaMaterial(C.Structure):
                 ('code', TinaInstr * TINA_MAX_INSTR)]
 
 
+(SNODE_LAMBERT, SNODE_PHONG, SNODE_COOK, SNODE_EMISSION, SNODE_MIX, SNODE_SCALE, SNODE_ADD) = range(7)
+TINA_SAMPLE_MAX_NODES, TINA_SAMPLE_MAX_INSTR = 16, 48
+
+
+class TinaSampleNode(C.Structure):
+    _fields_ = [('kind', C.c_int32), ('a', C.c_int32), ('b', C.c_int32), ('p0', C.c_int32), ('n0', C.c_int32),
+                ('p1', C.c_int32), ('n1', C.c_int32), ('pad_', C.c_int32)]
+
+
+class TinaSampleMaterial(C.Structure):
+    _fields_ = [('nnodes', C.c_int32), ('ncode', C.c_int32), ('ntex', C.c_int32), ('pad_', C.c_int32),
+                ('tex', C.c_void_p * TINA_MAX_TEX),
+                ('tex_w', C.c_int32 * TINA_MAX_TEX), ('tex_h', C.c_int32 * TINA_MAX_TEX), ('tex_c', C.c_int32 * TINA_MAX_TEX),
+                ('nodes', TinaSampleNode * TINA_SAMPLE_MAX_NODES), ('code', TinaInstr * TINA_SAMPLE_MAX_INSTR)]
+
+
 # name -> (restype, argtypes); every symbol include/tina_b200.h declares
 _vp, _i, _i64, _u32, _f = C.c_void_p, C.c_int, C.c_int64, C.c_uint32, C.c_float
 _fp = C.POINTER(C.c_float)
@@ -106,6 +122,10 @@ SIGNATURES = {
     'tina_image_tonemap': (_i, [_vp, _i64, _vp]),
     'tina_engine_ssao_render': (_i, [_vp, _vp, _vp, _i, _vp, _i, _f, _f, _f, _vp, _vp]),
     'tina_image_ssao_apply': (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    'tina_engine_ssao_render_taa': (_i, [_vp, _vp, _i, _f, _f, _f, _u32, _vp, _vp]),
+    'tina_image_ssao_apply_taa': (_i, [_vp, _vp, _i, _i, _vp]),
+    'tina_engine_ssr_render': (_i, [_vp, _vp, _vp, _vp, C.POINTER(TinaSampleMaterial), _i, _vp, _i, _i, _f, _f, _i, _i, _u32, _vp, _vp]),
+    'tina_image_ssr_apply': (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     'tina_image_fxaa': (_i, [_vp, _i, _i, _vp, _vp, _f, _f, _f, _vp]),
     'tina_image_bloom': (_i, [_vp, _i, _i, _vp, _vp, _vp, _i, _f, _f, _f, _vp]),
     'tina_image_accumulate': (_i, [_vp, _vp, _i64, _i, _vp]),

@@ -604,3 +604,83 @@ def material_struct(material, device, fold=True, color_is_one=True):
         m.code[i].op, m.code[i].arg = op, arg
         m.code[i].c[0], m.code[i].c[1], m.code[i].c[2] = c
     return m, keep
+
+
+# ---- material.sample() trees for SSR (postp/ssr.py:78-80) ---------------------------------------------------------
+def _value_is_scalar(node):
+    """Does the reference evaluate this parameter node to a scalar?  (MixMaterial.sample averages a vector factor with
+    Vavg and takes a scalar one as it is, common.py:36-40.)"""
+    if isinstance(node, Param):
+        return np.ndim(node[None]) == 0
+    if isinstance(node, Const):
+        return np.ndim(node.value) == 0 or np.size(node.value) == 1
+    if isinstance(node, Texture):
+        return node.image.shape[2] == 1
+    if isinstance(node, FresnelFactor):
+        return all(_value_is_scalar(node.param(k)) for k in ('metallic', 'albedo', 'specular'))
+    return False
+
+
+def sample_struct(material, device):
+    """Material node graph -> (TinaSampleMaterial, keep-alive): the tree `material.sample(idir, nrm, sign, rng)` of
+    matr/material.py descends -- MixMaterial (:123-138), ScaleMaterial (:180-184), AddMaterial (:227-238) over the
+    Lambert (:398-405), Phong (:459-472), CookTorrance (:364-384) and Emission (:679-681) leaves -- in pre-order
+    (node 0 = root), every node parameter as a postfix value program."""
+    P = _Program()
+    nodes = []
+
+    def value(node):
+        start = len(P.code)
+        _emit_value(P, node)
+        return start, len(P.code) - start
+
+    def walk(m):
+        idx = len(nodes)
+        rec = dict(kind=0, a=0, b=0, p0=0, n0=0, p1=0, n1=0, pad_=0)
+        nodes.append(rec)
+        if isinstance(m, MixMaterial):
+            f = m.param('factor')
+            rec['kind'] = _lib.SNODE_MIX
+            rec['p0'], rec['n0'] = value(f)
+            rec['pad_'] = 1 if _value_is_scalar(f) else 0
+            rec['a'], rec['b'] = walk(m.mat1), walk(m.mat2)
+        elif isinstance(m, ScaleMaterial):
+            rec['kind'] = _lib.SNODE_SCALE
+            rec['p0'], rec['n0'] = value(m.param('factor'))
+            rec['a'] = walk(m.mat)
+        elif isinstance(m, AddMaterial):
+            rec['kind'] = _lib.SNODE_ADD
+            rec['a'], rec['b'] = walk(m.mat1), walk(m.mat2)
+        elif isinstance(m, Lambert):
+            rec['kind'] = _lib.SNODE_LAMBERT
+        elif isinstance(m, Phong):
+            rec['kind'] = _lib.SNODE_PHONG
+            rec['p0'], rec['n0'] = value(m.param('shineness'))
+        elif isinstance(m, CookTorrance):
+            rec['kind'] = _lib.SNODE_COOK
+            rec['p0'], rec['n0'] = value(m.param('roughness'))
+            rec['p1'], rec['n1'] = value(m.param('fresnel'))
+        elif isinstance(m, Emission):
+            rec['kind'] = _lib.SNODE_EMISSION
+        else:
+            raise NotImplementedError(f'material {type(m).__name__} has no sample() on the B200 raster path')
+        return idx
+
+    walk(material)
+    if len(nodes) > _lib.TINA_SAMPLE_MAX_NODES or len(P.code) > _lib.TINA_SAMPLE_MAX_INSTR:
+        raise NotImplementedError(f'material too large for SSR ({len(nodes)} nodes, {len(P.code)} parameter instructions)')
+    out = _lib.TinaSampleMaterial()
+    out.nnodes, out.ncode, out.ntex = len(nodes), len(P.code), len(P.textures)
+    for i, rec in enumerate(nodes):
+        for key, v in rec.items():
+            setattr(out.nodes[i], key, v)
+    for i, (op, arg, c) in enumerate(P.code):
+        out.code[i].op, out.code[i].arg = op, arg
+        out.code[i].c[0], out.code[i].c[1], out.code[i].c[2] = c
+    keep = []
+    for i, t in enumerate(P.textures):
+        dt = t.device_tensor(device)
+        keep.append(dt)
+        out.tex[i] = dt.data_ptr()
+        out.tex_w[i], out.tex_h[i], out.tex_c[i] = dt.shape
+    return out, keep

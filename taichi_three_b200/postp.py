@@ -1,6 +1,6 @@
-"""Image-space post effects on the raster path's image: FXAA, Blooming and SSAO (reference tina/postp/fxaa.py,
-tina/postp/blooming.py, tina/postp/ssao.py) over tina_image_fxaa / tina_image_bloom / tina_engine_ssao_render of
-libtina_b200."""
+"""Image-space post effects on the raster path's image: FXAA, Blooming, SSAO and SSR (reference tina/postp/fxaa.py,
+tina/postp/blooming.py, tina/postp/ssao.py, tina/postp/ssr.py) over tina_image_fxaa / tina_image_bloom /
+tina_engine_ssao_render / tina_engine_ssr_render of libtina_b200."""
 import ctypes as C
 
 import numpy as np
@@ -81,8 +81,10 @@ class SSAO:
     world-normal G-buffer.  The tables are plain tensors (`samples`, `rotations`) and may be overwritten."""
 
     def __init__(self, res, norm, nsamples=64, thresh=0.0, radius=0.2, factor=1.0, noise_size=4, taa=False, seed=None):
-        if taa:
-            raise NotImplementedError('SSAO(taa=True) draws fresh random samples per pixel and frame; only the table mode is implemented')
+        # taa=True (ssao.py:52-56, 80-81): fresh samples per pixel and frame; the reference draws them from Taichi's
+        # unspecified ti.random(), here from the Wang hash of tina/random.py seeded with (pixel, frame)
+        self.taa = bool(taa)
+        self.frame = 0
         self.res = (int(res[0]), int(res[1]))
         self.norm = norm
         self.radius = HostField(np.float32(radius))
@@ -114,6 +116,13 @@ class SSAO:
         n = self.norm.to_torch() if hasattr(self.norm, 'to_torch') else self.norm
         if n.dtype != torch.float32 or not n.is_contiguous() or tuple(n.shape) != (self.res[0], self.res[1], 3):
             raise ValueError('SSAO needs a contiguous float32 [W, H, 3] normal buffer')
+        if self.taa:
+            _lib.check(_lib.lib().tina_engine_ssao_render_taa(engine._h, C.c_void_p(n.data_ptr()), self.nsamples, float(self.radius[None]),
+                                                              float(self.thresh[None]), float(self.factor[None]), self.frame & 0xffffffff,
+                                                              C.c_void_p(self.img.to_torch().data_ptr()), _stream()))
+            self.frame += 1
+            self._keep = (n,)
+            return
         smp, rot = self.samples.contiguous(), self.rotations.contiguous()
         _lib.check(_lib.lib().tina_engine_ssao_render(engine._h, C.c_void_p(n.data_ptr()), C.c_void_p(smp.data_ptr()), int(smp.shape[0]),
                                                       C.c_void_p(rot.data_ptr()), int(rot.shape[0]), float(self.radius[None]),
@@ -123,5 +132,69 @@ class SSAO:
 
     def apply(self, out):  # ssao.py:38-49
         t = _img(out)
+        if self.taa:
+            _lib.check(_lib.lib().tina_image_ssao_apply_taa(C.c_void_p(t.data_ptr()), C.c_void_p(self.img.to_torch().data_ptr()), t.shape[0],
+                                                            t.shape[1], _stream()))
+            return
         _lib.check(_lib.lib().tina_image_ssao_apply(C.c_void_p(t.data_ptr()), C.c_void_p(self.img.to_torch().data_ptr()), t.shape[0],
                                                     t.shape[1], self.noise_size, _stream()))
+
+
+class SSR:
+    """Screen-space reflections (postp/ssr.py): per pixel with a normal, `nsamples` rays drawn with `material.sample()`
+    of the pixel's material and marched through the depth buffer for at most `nsteps` steps; a hit adds the image colour
+    there times the sample weight.  norm / coor / mtlid are the scene's G-buffers (scene/raster.py:51-64), mtltab its
+    MaterialTable.  Non-TAA: the reference's WangHashRNG(P % blurring) stream (ssr.py:73-76), reproduced exactly; taa:
+    the same hash seeded with (pixel, frame) instead of Taichi's unspecified ti.random()."""
+
+    def __init__(self, res, norm, coor, mtlid, mtltab, taa=False):  # ssr.py:7-28
+        self.res = (int(res[0]), int(res[1]))
+        self.norm, self.coor, self.mtlid, self.mtltab, self.taa = norm, coor, mtlid, mtltab, bool(taa)
+        dev = (norm.to_torch() if hasattr(norm, 'to_torch') else norm).device
+        from .field import Field
+        self.img = Field(torch.zeros(self.res + (4,), dtype=torch.float32, device=dev))
+        self.nsamples = HostField(np.int32(32 if not taa else 12))
+        self.nsteps = HostField(np.int32(32 if not taa else 64))
+        self.stepsize = HostField(np.float32(2))
+        self.tolerance = HostField(np.float32(15))
+        self.blurring = HostField(np.int32(4))
+        self.frame = 0
+
+    def render(self, engine, image):  # ssr.py:44-103
+        from .material import sample_struct
+        t = _img(image)
+        W, H = self.res
+        n = self.norm.to_torch() if hasattr(self.norm, 'to_torch') else self.norm
+        m = self.mtlid.to_torch() if hasattr(self.mtlid, 'to_torch') else self.mtlid
+        c = None
+        if self.coor is not None:
+            c = self.coor.to_torch() if hasattr(self.coor, 'to_torch') else self.coor
+            if tuple(c.shape) != (W, H, 2):  # the reference's dummy (1, 1) field when the scene has no texturing (raster.py:63-64)
+                c = None
+        if n.dtype != torch.float32 or not n.is_contiguous() or tuple(n.shape) != (W, H, 3):
+            raise ValueError('SSR needs a contiguous float32 [W, H, 3] normal buffer')
+        if m.dtype != torch.int32 or not m.is_contiguous() or tuple(m.shape) != (W, H):
+            raise ValueError('SSR needs a contiguous int32 [W, H] material-id buffer')
+        if c is not None and (c.dtype != torch.float32 or not c.is_contiguous()):
+            raise ValueError('SSR needs a contiguous float32 [W, H, 2] texcoord buffer')
+        mats = list(self.mtltab.materials)
+        if not mats:
+            raise ValueError('SSR: the material table is empty')
+        table = (_lib.TinaSampleMaterial * len(mats))()
+        keep = []
+        for i, mat in enumerate(mats):
+            table[i], k = sample_struct(mat, n.device)
+            keep.append(k)
+        _lib.check(_lib.lib().tina_engine_ssr_render(
+            engine._h, C.c_void_p(n.data_ptr()), C.c_void_p(c.data_ptr()) if c is not None else None, C.c_void_p(m.data_ptr()), table,
+            len(mats), C.c_void_p(t.data_ptr()), int(self.nsamples[None]), int(self.nsteps[None]), float(self.stepsize[None]),
+            float(self.tolerance[None]), int(self.blurring[None]), int(self.taa), self.frame & 0xffffffff,
+            C.c_void_p(self.img.to_torch().data_ptr()), _stream()))
+        if self.taa:
+            self.frame += 1
+        self._keep = (n, m, c, keep, t)
+
+    def apply(self, image):  # ssr.py:30-42
+        t = _img(image)
+        _lib.check(_lib.lib().tina_image_ssr_apply(C.c_void_p(t.data_ptr()), C.c_void_p(self.img.to_torch().data_ptr()), t.shape[0], t.shape[1],
+                                                   int(self.blurring[None]), int(self.taa), _stream()))

@@ -1,7 +1,7 @@
 """Scene: frame orchestration for the raster pipeline (reference tina/scene/raster.py:5-258),
 restricted to the triangle-raster path: objects -> set_object / render_occup / render_color,
-default light + ambient, ACES tonemap, and the image-space passes ssao / blooming / fxaa / taa in the reference's
-order.  Options that enable other subsystems (ibl, ssr) raise."""
+default light + ambient, ACES tonemap, and the image-space passes ssao / ssr / blooming / fxaa / taa in the reference's
+order.  Options that enable other subsystems (ibl) raise."""
 import numpy as np
 import torch
 
@@ -39,8 +39,21 @@ class Accumator:
                                                     self.count[0], _stream()))
 
 
+class MaterialTable:
+    """The scene's materials by id (matr/material.py:643-656); SSR looks a pixel's material up by its mtlid."""
+
+    def __init__(self):
+        self.materials = []
+
+    def clear_materials(self):
+        self.materials.clear()
+
+    def add_material(self, matr):
+        self.materials.append(matr)
+
+
 class Scene:
-    UNSUPPORTED = ('ibl', 'ssr')
+    UNSUPPORTED = ('ibl',)
 
     def __init__(self, res_x=512, res_y=None, **options):
         self.engine = Engine(res_x, res_y)
@@ -70,13 +83,29 @@ class Scene:
             from .postp import FXAA
             self.fxaa = FXAA(self.res)
         self.ssao = options.get('ssao', False)
-        if self.ssao:  # raster.py:51-54, 65-66: world-normal G-buffer as a pre-shader + the SSAO pass
-            from .postp import SSAO
+        self.ssr = options.get('ssr', False)
+        dev = self.engine.device
+        if self.ssr:  # raster.py:43-49: the materials by id, for SSR's material.sample()
+            self.mtltab = MaterialTable()
+        if self.ssao or self.ssr:  # raster.py:51-54: world-normal G-buffer as a pre-shader
             from .shader import NormalShader
-            self.norm_buffer = Field(torch.zeros((self.res[0], self.res[1], 3), dtype=torch.float32, device=self.engine.device))
+            self.norm_buffer = Field(torch.zeros((self.res[0], self.res[1], 3), dtype=torch.float32, device=dev))
             self.norm_shader = NormalShader(self.norm_buffer)
             self.pre_shaders.append(self.norm_shader)
+        if self.ssr:  # raster.py:56-64: material ids (a ConstShader per material) and, with texturing, texture coordinates
+            from .shader import TexcoordShader
+            self.mtlid_buffer = Field(torch.zeros(self.res, dtype=torch.int32, device=dev))
+            self.coor_buffer = None
+            if 'texturing' in options:
+                self.coor_buffer = Field(torch.zeros((self.res[0], self.res[1], 2), dtype=torch.float32, device=dev))
+                self.coor_shader = TexcoordShader(self.coor_buffer)
+                self.pre_shaders.append(self.coor_shader)
+        if self.ssao:  # raster.py:65-66
+            from .postp import SSAO
             self.ssao = SSAO(self.res, self.norm_buffer, taa=self.taa)
+        if self.ssr:  # raster.py:68-70
+            from .postp import SSR
+            self.ssr = SSR(self.res, self.norm_buffer, self.coor_buffer, self.mtlid_buffer, self.mtltab, taa=self.taa)
         if self.taa:
             self.accum = Accumator(self.res, self.engine.device)
         # raster.py:90-93
@@ -87,8 +116,13 @@ class Scene:
         if any(material is m for m in self.materials):
             return
         shader = Shader(self.image, self.lighting, material)
+        base_shaders = [shader]
+        if self.ssr:  # raster.py:102-105 (the table itself is filled by a materialize callback there, :45-49)
+            from .shader import ConstShader
+            base_shaders.append(ConstShader(self.mtlid_buffer, len(self.materials)))
+            self.mtltab.add_material(material)
         self.materials.append(material)
-        self.shaders[id(material)] = ShaderGroup(self.pre_shaders + [shader] + self.post_shaders)
+        self.shaders[id(material)] = ShaderGroup(self.pre_shaders + base_shaders + self.post_shaders)
 
     def add_object(self, object, material=None, raster=None):  # raster.py:112-146
         assert id(object) not in self.objects
@@ -148,8 +182,8 @@ class Scene:
         # Frame glue folded into the shading passes (results identical to the separate passes):
         #  * image.fill(bg) rides along with the FIRST object's pass (every rasteriser that takes fill_bg);
         #  * the ACES curve and the TAA accumulation ride along with the LAST object's pass when that is a triangle pass
-        #    and nothing sits between shading and tonemap (no SSAO / blooming): it finishes the pixels it does not own too.
-        post_free = not self.blooming and not self.ssao and getattr(self, 'fuse_glue', True)  # (fuse_glue = False: separate passes)
+        #    and nothing sits between shading and tonemap (no SSAO / SSR / blooming): it finishes the pixels it does not own too.
+        post_free = not self.blooming and not self.ssao and not self.ssr and getattr(self, 'fuse_glue', True)  # (fuse_glue = False: separate passes)
         last_fuses = bool(items) and fuses(items[-1][1].raster) and post_free
         fuse_tm = bool(self.tonemap) and (last_fuses or (len(items) == 1 and post_free and hasattr(items[0][1].raster, 'set_particles')))
         fuse_acc = bool(self.taa) and last_fuses and not self.fxaa
@@ -172,6 +206,9 @@ class Scene:
         if self.ssao:  # raster.py:189-191
             self.ssao.render(self.engine)
             self.ssao.apply(self.image)
+        if self.ssr:  # raster.py:192-194
+            self.ssr.render(self.engine, self.image)
+            self.ssr.apply(self.image)
         if self.blooming:  # raster.py:200-201
             self.blooming.apply(self.image)
         if self.tonemap and not fuse_tm:

@@ -304,6 +304,31 @@ def test_oracle_material_front_end_is_independent_and_agrees(O, tina):
     assert bytes(a) == bytes(b) == bytes(L.struct())
 
 
+def test_sample_trees_of_product_and_oracle_agree(O, tina):
+    """material.sample() trees for SSR: the product's flattener (material.sample_struct) and the oracle's own walker
+    (oracle/materials.sample_pod_of) produce the same nodes and parameter programs; a scalar mix factor is marked."""
+    import torch
+    from oracle import materials as OM
+    from taichi_three_b200.material import sample_struct
+    img = np.random.default_rng(1).random((4, 4, 3)).astype(np.float32)
+    graphs = [tina.Diffuse(), tina.Classic(), tina.PBR(), tina.Lamp(), tina.PBR(basecolor=tina.Texture(img), metallic=0.3, roughness=0.2),
+              (tina.Classic(shineness=8) * 0.5 + tina.Lamp(color=[1, 0, 0])).mix(tina.PBR(metallic=1.0), [0.2, 0.4, 0.6])]
+    for g in graphs:
+        a, _ = sample_struct(g, torch.device('cpu'))
+        b, _ = OM.sample_pod_of(g)
+        assert (a.nnodes, a.ncode, a.ntex) == (b.nnodes, b.ncode, b.ntex)
+        for i in range(a.nnodes):
+            assert all(getattr(a.nodes[i], k) == getattr(b.nodes[i], k) for k in ('kind', 'a', 'b', 'p0', 'n0', 'p1', 'n1', 'pad_'))
+        for i in range(a.ncode):
+            assert (a.code[i].op, a.code[i].arg, tuple(a.code[i].c)) == (b.code[i].op, b.code[i].arg, tuple(b.code[i].c))
+    a, _ = sample_struct(tina.Classic(), torch.device('cpu'))
+    assert a.nodes[0].kind == 4 and a.nodes[0].pad_ == 1  # Classic: MixMaterial with the scalar factor 0.4
+    a, _ = sample_struct(graphs[-1], torch.device('cpu'))
+    assert a.nodes[0].pad_ == 0  # a vector factor is averaged (Vavg)
+    with pytest.raises(NotImplementedError):
+        sample_struct(object(), torch.device('cpu'))
+
+
 def test_bench_reference_arm_is_product_free_and_uses_every_core():
     """`bench.py --impl reference` under torchrun's OMP_NUM_THREADS=1: every host core, the same config object as the
     GPU arm, and no product module (nor libtina_b200.so) in the process."""
