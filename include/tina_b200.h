@@ -276,7 +276,10 @@ int tina_raster_buffers(TinaRaster *r, const float **verts, const float **norms,
  * 16 = plain square MeshGrid sources: independent persistent warps over row chunks staged through shared memory by
  *      cp.async (k_raster_grid; default 0: measured slower than the gather kernel every indexed source uses),
  * 17 = plain square MeshGrid sources: one quad (two faces, four vertex records) per thread (k_raster_quads, default 1);
- *      0 = one face per thread like every other indexed source */
+ *      0 = one face per thread like every other indexed source,
+ * 18 = indexed sources: when no set_faces* call happened since the previous render_occup, the vertex-stage blocks of this
+ *      one do not wait for the previous render_color (they write the other of two per-vertex record sets; the blocks that
+ *      clear the keys still wait), so consecutive frames overlap by that kernel's last wave (default 1) */
 int tina_raster_set_tuning(TinaRaster *r, int which, int value);
 /* counters of the last render_occup (synchronises): faces culled, clipped, per-thread,
  * per-warp, queued for the tile path, tile-list entries */

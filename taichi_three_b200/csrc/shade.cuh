@@ -599,6 +599,11 @@ k_render_color(const long long *__restrict__ keys, const float *__restrict__ ver
     static_assert((1 << FLAG_SHIFT) % K4_THREADS == 0 && (K4_THREADS * 3) % 4 == 0, "a K4 block lies inside one coverage chunk");
     float *const acc = GLUE ? acc_rt : nullptr;
     pdl_wait();
+#ifndef K4_NO_TRIGGER
+    // the rasteriser is complete: the next frame's vertex stage may start on the SMs this kernel's tail leaves idle (its
+    // vertex blocks write the other record set and do not wait; its clear blocks wait for this grid to finish)
+    pdl_launch_dependents();
+#endif
     if (blockIdx.x == 0 && threadIdx.x == 0 && publish) { // tell the host how many faces needed the tile path
         // running counts live in device memory; the mapped host words are only written (posted stores, no PCIe
         // round trip).  The host reads them as a heuristic, a stale value is harmless.

@@ -160,8 +160,12 @@ struct IndexedState {
     int64_t a_nout;
     // owned per-vertex buffers
     float *vpos_w, *vnrm_w;
-    float4 *recA; // per-vertex records, written by k_frame_prologue in render_occup (raster_indexed.cuh)
-    uint4 *recB;
-    int64_t vpos_cap, vnrm_cap, recA_cap, recB_cap, nv, nvn;
+    // per-vertex records, written by k_frame_prologue in render_occup (raster_indexed.cuh).  Two sets used by alternate
+    // render_occup calls: the vertex stage of the next call may then run while the shading kernel of this one still
+    // reads its records (programmatic dependent launch, see k_frame_prologue); recA / recB = the set of the last call
+    float4 *recA, *recA2[2];
+    uint4 *recB, *recB2[2];
+    unsigned rec_parity;
+    int64_t vpos_cap, vnrm_cap, recA_cap[2], recB_cap[2], nv, nvn;
     int force_general; // tuning knob 15: mark every vertex non-tame (every face takes K1's general path)
 };

@@ -968,6 +968,50 @@ def test_ssao_matches_reference_golden_and_scene_option(tina, O):
     assert np.abs(scene.img.to_numpy() - expect).max() <= 1e-6
 
 
+def test_consecutive_frames_overlap_without_interference(tina, O):
+    """Frames rendered back to back with nothing between them: the vertex stage of frame k + 1 (which does not wait for
+    frame k's shading kernel and writes the other per-vertex record set) must not disturb frame k.  Eight cameras, one
+    scene and raster, one image per frame; every image and key buffer equals the frame rendered in isolation."""
+    import torch
+    W, H, n = 640, 360, 256
+    scene = tina.Scene((W, H), smoothing=True, maxfaces=2**18, tonemap=False)
+    mesh = tina.MeshGrid(n)
+    mesh.pos.from_numpy(scenes.wave_grid_pos(n))
+    mat = tina.Classic()
+    scene.add_object(mesh, mat)
+    raster = scene.triangle_raster
+    raster.set_object(mesh)
+    cams = [tina.orbit_camera(radius=3.0, theta=0.1 * k, phi=0.07 * k, aspect=W / H) for k in range(8)]
+    imgs = [tina.Field(torch.zeros((W, H, 3), device='cuda')) for _ in cams]
+    shaders = [tina.Shader(im, scene.lighting, mat) for im in imgs]
+    bg = np.zeros(3, np.float32)
+
+    def frame(k):
+        scene.engine.set_camera(*cams[k])
+        scene.engine.clear_depth()
+        raster.render_occup()
+        raster.render_color(shaders[k], fill_bg=bg)
+    ref = []
+    for k in range(len(cams)):  # isolated frames
+        frame(k)
+        torch.cuda.synchronize()
+        ref.append((imgs[k].to_numpy().copy(), scene.engine.keys.clone()))
+        imgs[k].to_torch().zero_()
+    torch.cuda.synchronize()
+    for rep in range(5):
+        for k in range(len(cams)):  # back to back, no synchronisation, no other kernel between the frames
+            frame(k)
+        torch.cuda.synchronize()
+        for k in range(len(cams)):
+            assert np.array_equal(imgs[k].to_numpy(), ref[k][0]), (rep, k)
+        assert torch.equal(scene.engine.keys, ref[-1][1])
+    raster.set_tuning(overlap_vertex=0)
+    for k in range(len(cams)):
+        frame(k)
+    torch.cuda.synchronize()
+    assert all(np.array_equal(imgs[k].to_numpy(), ref[k][0]) for k in range(len(cams)))
+
+
 def _ssr_close(a, b, tol=2e-5, max_outliers=0.01):
     """SSR fields agree: every value within tol except for isolated pixels where one ray-march test (a hard `<`) flipped
     on the last ulp of sinf / cosf / powf; those are counted, and bounded."""
