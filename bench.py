@@ -406,11 +406,16 @@ def c5_measure(env, K, warmup, nfaces=None):
                step_ms_min_median_max=[float(step_ms.min()), float(np.median(step_ms)), float(step_ms.max())],
                composite='keys MIN over peer key buffers inside k_render_color (NVLink loads), image strips stored to rank 0' if world > 1 else 'single GPU',
                # every rank reads its strip of the other ranks' keys; every rank but the root stores its image strip to the root
-               nvlink_bytes_per_frame=(world - 1) * W * H * 8 + (world - 1) * W * H * 12 // world)
+               nvlink_bytes_per_frame=0)
     # checksums that must not depend on the number of GPUs: the composited image (complete on rank 0) and, per strip
     # owner, the composited keys of its strip
     npix = W * H
-    lo, hi = M.strip_range(npix, env['rank'], world) if world > 1 and npix % (256 * world) == 0 else (0, npix)
+    lo, hi, share = M.sort_last_strip(npix, env['rank'], world) if world > 1 and npix % (256 * world) == 0 else (0, npix, 1.0)
+    if world > 1:
+        r_lo, r_hi, _ = M.sort_last_strip(npix, 0, world)
+        out['root_strip_share'] = (r_hi - r_lo) / npix
+        # every rank reads its strip of the other ranks' keys; every rank but the root stores its image strip to the root
+        out['nvlink_bytes_per_frame'] = (world - 1) * npix * 8 + (npix - (r_hi - r_lo)) * 12
     ks = k.view(-1)[lo:hi]
     ksum = torch.stack([(ks ^ (ks >> 29)).sum(), ((ks & 0xffffffff) != 0).sum()])
     if world > 1:

@@ -53,11 +53,31 @@ def composite_min(keys, group=None):
     return keys
 
 
-def strip_range(npix, rank, world):
-    """Contiguous pixel strip [lo, hi) of `rank` (x-major pixel indices, multiples of 256)."""
+def strip_range(npix, rank, world, root=None, root_share=1.0):
+    """Contiguous pixel strip [lo, hi) of `rank` (x-major pixel indices, multiples of 256).  root / root_share: the
+    rank that also receives everybody's image strips takes `root_share` of an equal share (0 = it shades nothing), so
+    that the keys it reads and the image strips it receives do not pile up on its one NVLink port."""
     nblk = (npix + 255) // 256
-    per = (nblk + world - 1) // world
-    return min(rank * per * 256, npix), min((rank + 1) * per * 256, npix)
+    if root is None or root_share == 1.0 or world < 2:
+        per = (nblk + world - 1) // world
+        return min(rank * per * 256, npix), min((rank + 1) * per * 256, npix)
+    w = [float(root_share) if r == root else 1.0 for r in range(world)]
+    tot = sum(w)
+    edge = lambda r: int(round(sum(w[:r]) / tot * nblk))  # noqa: E731
+    lo, hi = (0 if rank == 0 else edge(rank)), (nblk if rank == world - 1 else edge(rank + 1))
+    return min(lo * 256, npix), min(hi * 256, npix)
+
+
+def sort_last_strip(npix, rank, world, composite='p2p', gather='root', root_share=None):
+    """The strip render_sort_last_replicated gives `rank` (same defaults): -> (lo, hi, root_share used)."""
+    if root_share is None:
+        import os
+        env = os.environ.get('TINA_ROOT_SHARE')  # experiments
+        root_share = float(env) if env is not None else (0.0 if (world >= 4 and composite == 'p2p' and gather == 'root') else 1.0)
+    if not (composite == 'p2p' and gather == 'root'):
+        root_share = 1.0  # (the collectives need equal strips)
+    lo, hi = strip_range(npix, rank, world, root=0, root_share=root_share)
+    return lo, hi, root_share
 
 
 class SharedImage:
@@ -95,7 +115,8 @@ class SharedImage:
             self._ptr = None
 
 
-def render_sort_last_replicated(engine, raster, verts, norms, coors, shader, bgcolor=0.0, group=None, composite='nccl', gather='all'):
+def render_sort_last_replicated(engine, raster, verts, norms, coors, shader, bgcolor=0.0, group=None, composite='nccl', gather='all',
+                                root_share=None):
     """Sort-last frame with REPLICATED face attributes (every rank holds all N faces, C5: 4.8 GB):
     rank r rasterises faces face_range(N, r, G) with global ids, the keys are MIN-reduce-scattered so
     rank r ends up with the final keys of screen strip r (1/G of the all-reduce traffic), shades that
@@ -107,7 +128,9 @@ def render_sort_last_replicated(engine, raster, verts, norms, coors, shader, bgc
     peer memory inside the kernel (TriangleRaster.render_color_composite).  Same bits.
 
     gather='root' (shader.img wraps a SharedImage tensor): the image is assembled on the root rank only, by the
-    shading kernels' own stores over NVLink; no all-gather."""
+    shading kernels' own stores over NVLink; no all-gather.  root_share (p2p + root only): the share of an equal strip
+    rank 0 takes (default 0 from 4 ranks on: the root's NVLink port already receives every other rank's image strip --
+    348 MB at 8K on 8 GPUs -- and would read 7/8 of its own strip's keys through it as well)."""
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     N = verts.shape[0]
@@ -130,7 +153,7 @@ def render_sort_last_replicated(engine, raster, verts, norms, coors, shader, bgc
     if raster.texturing:
         raster.set_face_coors(coors)
     if world > 1 and npix % (256 * world) == 0:
-        p_lo, p_hi = strip_range(npix, rank, world)
+        p_lo, p_hi, _ = sort_last_strip(npix, rank, world, composite, gather, root_share)
         if composite == 'p2p':
             # a one-word all-reduce on the same stream: it completes on this rank only after every rank has
             # enqueued it behind its own render_occup (dist.barrier() would also block the host)

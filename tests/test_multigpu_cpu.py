@@ -88,3 +88,10 @@ def test_strip_ranges_tile_the_screen():
         assert r[0][0] == 0 and r[-1][1] == npix
         assert all(r[i][1] == r[i + 1][0] for i in range(w - 1))
         assert all(lo % 256 == 0 for lo, hi in r if lo < npix)
+        for share in (0.0, 0.5):  # the image root takes a smaller strip (sort-last over peer memory)
+            r = [M.strip_range(npix, k, w, root=0, root_share=share) for k in range(w)]
+            assert r[0][0] == 0 and r[-1][1] == npix and all(r[i][1] == r[i + 1][0] for i in range(w - 1))
+            assert all(lo % 256 == 0 for lo, hi in r if lo < npix)
+            if share == 0.0:
+                assert r[0] == (0, 0)
+    assert M.sort_last_strip(7680 * 4320, 0, 8)[:2] == (0, 0) and M.sort_last_strip(7680 * 4320, 0, 2)[2] == 1.0
