@@ -677,12 +677,14 @@ k_render_color(const long long *__restrict__ keys, const float *__restrict__ ver
         // sort-last composite fused into the shading pass: the winner of this pixel is the MIN of the packed keys
         // of every rank, read straight from the peers' key buffers over NVLink (L2-coherent loads: a peer's buffer
         // changes between frames, L1 must not keep it); the composited key is kept in the local buffer
-        long long k = __ldcg(peers.p[0] + P);
-#pragma unroll 1
-        for (int q = 1; q < peers.n; q++) {
-            const long long o = __ldcg(peers.p[q] + P);
-            k = o < k ? o : k;
-        }
+        // every peer's key is requested before the first one is used: one NVLink round trip per pixel instead of one per
+        // peer (the loop form issued them one after the other)
+        long long kk[TINA_MAX_PEERS];
+#pragma unroll
+        for (int q = 0; q < TINA_MAX_PEERS; q++) kk[q] = q < peers.n ? __ldcg(peers.p[q] + P) : 0x7fffffffffffffffll;
+        long long k = kk[0];
+#pragma unroll
+        for (int q = 1; q < TINA_MAX_PEERS; q++) k = kk[q] < k ? kk[q] : k;
         keys_out[P] = k;
         id = (unsigned)(unsigned long long)k;
     } else {
