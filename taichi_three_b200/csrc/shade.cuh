@@ -586,7 +586,9 @@ struct PeerTab {
 
 // GLUE: the instantiations that can finish other objects' pixels (TINA_COLOR_FINISH) and accumulate (TAA); the
 // plain ones compile those paths away (carrying them as run-time options cost the C2 frame 2 us).
-template <int KIND, bool IDX, bool FAST, int LEAN = 0, bool GLUE = false>
+// COMP: the sort-last composite over peer memory (keys = MIN over every rank's buffer, image strip stored into the
+// root rank's image): its own instantiations, so that the plain kernels carry none of it.
+template <int KIND, bool IDX, bool FAST, int LEAN = 0, bool GLUE = false, bool COMP = false>
 __global__ void __launch_bounds__(K4_THREADS, K4_MINBLOCKS)
 k_render_color(const long long *__restrict__ keys, const float *__restrict__ verts, const float *__restrict__ norms,
                const float *__restrict__ coors, const __grid_constant__ Cam cam, uint32_t flags, unsigned base,
@@ -670,26 +672,51 @@ k_render_color(const long long *__restrict__ keys, const float *__restrict__ ver
         return;
     }
     const long long Pl = p0 + threadIdx.x;
+    if (COMP) {
+        // Sort-last composite fused into the shading pass: the winner of a pixel is the MIN of the packed keys of every
+        // rank, read straight from the peers' key buffers over NVLink (L2-coherent loads: a peer's buffer changes between
+        // frames, L1 must not keep it); every peer's key is requested before the first one is used (one round trip per
+        // pixel, not one per peer); the composited key is kept in the local buffer.
+        // The image usually lives on another GPU too (SharedImage on the root rank).  Three 4-byte stores per pixel
+        // cross NVLink as partially filled sectors -- 0.97 ms for a 57 MB strip on 8 GPUs, twice what the root's port needs
+        // for all seven strips (tools/c5_breakdown.py) -- so the CTA stages its 3 KB in shared memory and sends whole
+        // 16-byte pieces, as long as every pixel of the CTA has a colour (a face, or the background fill).
+        __shared__ __align__(16) float simg[K4_THREADS * 3];
+        const bool valid = Pl < npix;
+        const int P = valid ? (int)Pl : 0;
+        bool have = false;
+        float cr = r, cg = g, cb = b;
+        if (valid) {
+            long long kk[TINA_MAX_PEERS];
+#pragma unroll
+            for (int q = 0; q < TINA_MAX_PEERS; q++) kk[q] = q < peers.n ? __ldcg(peers.p[q] + P) : 0x7fffffffffffffffll;
+            long long k = kk[0];
+#pragma unroll
+            for (int q = 1; q < TINA_MAX_PEERS; q++) k = kk[q] < k ? kk[q] : k;
+            keys_out[P] = k;
+            const unsigned idc = (unsigned)(unsigned long long)k, fidc = idc - 1u - base;
+            if (idc == 0u || fidc >= nfaces) {
+                have = fill;
+            } else {
+                V3 c = shade_pixel<KIND, IDX, FAST, LEAN>(P, fidc, verts, norms, coors, cam, flags, mat, L, S);
+                if (cflags & TINA_COLOR_TONEMAP) c.x = aces_t<FAST>(c.x), c.y = aces_t<FAST>(c.y), c.z = aces_t<FAST>(c.z);
+                cr = c.x, cg = c.y, cb = c.z, have = true;
+            }
+        }
+        simg[threadIdx.x * 3] = cr, simg[threadIdx.x * 3 + 1] = cg, simg[threadIdx.x * 3 + 2] = cb;
+        const bool whole = __syncthreads_and(have && valid) && (((uintptr_t)image) & 15) == 0; // (p0 * 12 is a multiple of 16)
+        if (whole) {
+            if (threadIdx.x < K4_THREADS * 3 / 4)
+                __stcs(reinterpret_cast<float4 *>(image + p0 * 3) + threadIdx.x, reinterpret_cast<const float4 *>(simg)[threadIdx.x]);
+        } else if (have && valid) {
+            float *o = image + (long long)P * 3;
+            __stcs(o, cr), __stcs(o + 1, cg), __stcs(o + 2, cb);
+        }
+        return;
+    }
     if (Pl >= npix) return;
     const int P = (int)Pl;
-    unsigned id;
-    if (peers.n > 1) {
-        // sort-last composite fused into the shading pass: the winner of this pixel is the MIN of the packed keys
-        // of every rank, read straight from the peers' key buffers over NVLink (L2-coherent loads: a peer's buffer
-        // changes between frames, L1 must not keep it); the composited key is kept in the local buffer
-        // every peer's key is requested before the first one is used: one NVLink round trip per pixel instead of one per
-        // peer (the loop form issued them one after the other)
-        long long kk[TINA_MAX_PEERS];
-#pragma unroll
-        for (int q = 0; q < TINA_MAX_PEERS; q++) kk[q] = q < peers.n ? __ldcg(peers.p[q] + P) : 0x7fffffffffffffffll;
-        long long k = kk[0];
-#pragma unroll
-        for (int q = 1; q < TINA_MAX_PEERS; q++) k = kk[q] < k ? kk[q] : k;
-        keys_out[P] = k;
-        id = (unsigned)(unsigned long long)k;
-    } else {
-        id = (unsigned)(unsigned long long)__ldcs(keys + P);
-    }
+    const unsigned id = (unsigned)(unsigned long long)__ldcs(keys + P);
     const unsigned fid = id - 1u - base;
     float *out = image + (long long)P * 3;
     if (id == 0u || fid >= nfaces) { // triangle.py:137-138 (occup == -1)
