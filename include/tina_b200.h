@@ -302,6 +302,10 @@ int tina_pars_render_occup(TinaPars *r, void *stream);                    /* par
 int tina_pars_render_color(TinaPars *r, const TinaMaterial *mat_host, const TinaLighting *light_host, float *image,
                            uint32_t flags, const float *bg_host, void *stream); /* particle.py:129-161 */
 int tina_pars_occup(TinaPars *r, int32_t *occup, void *stream);
+/* G-buffer sinks for the current particles (particle.py:129-161 hands pos / normal / texcoord (0, 0) / colour of the visible
+ * sphere point to any shader of a ShaderGroup): same sink kinds and layout as tina_raster_render_gbuffers */
+int tina_pars_render_gbuffers(TinaPars *r, int nsinks, const int *kinds_host, void *const *outs_host, const int *ncomps_host,
+                              const int *out_is_int_host, const float *params_host, void *stream);
 
 /* ---- WireframeRaster (core/wireframe.py:4-95): depth-tested DDA lines on the same Engine ---- */
 typedef struct TinaWire TinaWire;

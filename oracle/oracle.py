@@ -123,6 +123,15 @@ def pars_color(verts, sizes, colors, occup, W2V, V2W, W, H, material, lighting, 
     return image
 
 
+def pars_attrs(verts, sizes, occup, W2V, V2W, W, H, bias=(0.5, 0.5)):
+    """core/particle.py:129-158: (pos, normal) [W, H, 3] of the visible sphere points (zero where occup == -1)."""
+    verts, sizes = _f(verts).reshape(-1, 3), _f(sizes).reshape(-1)
+    pos, nrm = np.zeros((W, H, 3), np.float32), np.zeros((W, H, 3), np.float32)
+    lib().orc_pars_attrs(_p(verts), _p(sizes), _p(np.ascontiguousarray(occup, dtype=np.int32)), _p(_f(W2V).reshape(16)),
+                         _p(_f(V2W).reshape(16)), _p(_f(bias)), W, H, _p(pos), _p(nrm))
+    return pos, nrm
+
+
 def render_color(verts, norms, coors, occup, W2V, V2W, W, H, flags, material, lighting, image, bias=(0.5, 0.5),
                  parallel=True):
     """Shades pixels with occup != -1 into `image` ([W,H,3] f32, modified in place and returned).

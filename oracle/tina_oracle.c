@@ -625,6 +625,31 @@ void orc_pars_color(const float *verts, const float *sizes, const float *colors,
         }
 }
 
+/* particle.py:129-158: the shader inputs of the visible sphere point (what a NormalShader / PositionShader in the
+ * particle's ShaderGroup receives); pos, normal: [W][H][3], written where occup != -1 */
+void orc_pars_attrs(const float *verts, const float *sizes, const int32_t *occup, const float *W2V, const float *V2W,
+                    const float *bias, int W, int H, float *pos, float *normal) {
+    float Zl[3];
+    mapply_dir_n(V2W, 0, 0, 1, Zl);
+    for (int x = 0; x < W; x++)
+        for (int y = 0; y < H; y++) {
+            int64_t P = (int64_t)x * H + y;
+            int32_t f = occup[P];
+            if (f == -1) continue;
+            const float *Al = verts + (int64_t)f * 3;
+            float Rl = sizes[f], Av[3];
+            mapply_pos(W2V, Al, Av);
+            float p[2] = {(float)x + bias[0], (float)y + bias[1]};
+            float Pv[3] = {p[0] / (float)W * 2.0f - 1.0f, p[1] / (float)H * 2.0f - 1.0f, Av[2]}, Pl[3], Dl[3];
+            mapply_pos(V2W, Pv, Pl);
+            for (int k = 0; k < 3; k++) Dl[k] = (Pl[k] - Al[k]) / Rl;
+            float t = sqrtf(1.0f - dot3(Dl, Dl));
+            for (int k = 0; k < 3; k++) Dl[k] = Dl[k] - Zl[k] * t;
+            normalize3(Dl);
+            for (int k = 0; k < 3; k++) normal[P * 3 + k] = Dl[k], pos[P * 3 + k] = Al[k] + Dl[k] * Rl;
+        }
+}
+
 /* ---- WireframeRaster (core/wireframe.py:49-95), serial order; flags: 2 = clipping.  verts [N][2][3].
  * On a depth win the pixel of `image` becomes img * (1 - 1) + color * 1 (Shader.blend_color, shader.py:133-135). */
 void orc_wire_render(const float *verts, int64_t nwires, const float *W2V, const float *bias, int W, int H, uint32_t flags,

@@ -113,6 +113,7 @@ SIGNATURES = {
     'tina_pars_render_occup': (_i, [_vp, _vp]),
     'tina_pars_render_color': (_i, [_vp, C.POINTER(TinaMaterial), C.POINTER(TinaLighting), _vp, _u32, _fp, _vp]),
     'tina_pars_occup': (_i, [_vp, _vp, _vp]),
+    'tina_pars_render_gbuffers': (_i, [_vp, _i, C.POINTER(_i), C.POINTER(_vp), C.POINTER(_i), C.POINTER(_i), _fp, _vp]),
     'tina_wire_create': (_i, [C.POINTER(_vp), _vp, _i64, _u32, _fp]),
     'tina_wire_destroy': (_i, [_vp]),
     'tina_wire_set_color': (_i, [_vp, _fp]),

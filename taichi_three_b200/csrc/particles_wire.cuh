@@ -153,6 +153,40 @@ k_pars_color(const long long *__restrict__ keys, const float *__restrict__ verts
     out[0] = c.x, out[1] = c.y, out[2] = c.z;
 }
 
+// G-buffer sinks for particles: ParticleRaster.render_color hands pos / normal / texcoord / color of the visible sphere
+// point to ANY shader (particle.py:129-161), e.g. the NormalShader of Scene(ssao=True) -- same inputs as k_pars_color
+__global__ void __launch_bounds__(256)
+k_pars_gbuffer(const long long *__restrict__ keys, const float *__restrict__ verts, const float *__restrict__ sizes,
+               const float *__restrict__ colors, const __grid_constant__ Cam cam, unsigned base, unsigned npars,
+               const __grid_constant__ SinkTab T) {
+    pdl_wait();
+    const int P = blockIdx.x * 256 + threadIdx.x;
+    if (P >= cam.W * cam.H) return;
+    const long long key = keys[P];
+    const unsigned id = (unsigned)(unsigned long long)key;
+    const unsigned f = id - 1u - base;
+    if (id == 0u || f >= npars) return; // particle.py:131-133
+    const int x = P / cam.H, y = P - x * cam.H;
+    ParSetup s;
+    s.ax = __ldg(verts + (long long)f * 3), s.ay = __ldg(verts + (long long)f * 3 + 1), s.az = __ldg(verts + (long long)f * 3 + 2);
+    s.rl = __ldg(sizes + f);
+    s.avz = mapply_pos3(cam.W2V, s.ax, s.ay, s.az).z;
+    V3 pl;
+    par_hit(s, cam, x, y, pl);
+    V3 d = v3((pl.x - s.ax) / s.rl, (pl.y - s.ay) / s.rl, (pl.z - s.az) / s.rl);
+    const V3 zl = axis_dir(cam.V2W, 0.f, 0.f, 1.f);
+    const float t = sqrtf(1.0f - dot3(d, d));
+    d = normalized(v3(d.x - zl.x * t, d.y - zl.y * t, d.z - zl.z * t));
+    ShadeIn in;
+    in.normal = d;
+    in.pos = v3(s.ax + d.x * s.rl, s.ay + d.y * s.rl, s.az + d.z * s.rl);
+    in.texcoord = v3(0.f, 0.f, 0.f);
+    in.color = colors ? v3(__ldg(colors + (long long)f * 3), __ldg(colors + (long long)f * 3 + 1), __ldg(colors + (long long)f * 3 + 2))
+                      : v3(1.f, 1.f, 1.f);
+    const float px = (float)x + cam.bias[0], py = (float)y + cam.bias[1];
+    write_sinks(T, P, key, f, in, px, py, view_direction(cam, px, py), cam);
+}
+
 // ------------------------------------------------------------------------------------
 // WireframeRaster (core/wireframe.py:70-95): depth-tested DDA lines on the engine's key buffer
 // ------------------------------------------------------------------------------------

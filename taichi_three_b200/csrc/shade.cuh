@@ -743,30 +743,9 @@ struct SinkTab {
     void *out[TINA_MAX_SINKS];
     float p[TINA_MAX_SINKS][3];
 };
-template <bool IDX>
-__global__ void __launch_bounds__(256)
-k_gbuffer(const long long *__restrict__ keys, const float *__restrict__ verts, const float *__restrict__ norms,
-          const float *__restrict__ coors, const __grid_constant__ Cam cam, uint32_t flags, unsigned base, unsigned nfaces,
-          const __grid_constant__ SinkTab T, const __grid_constant__ Src S) {
-    pdl_wait();
-    const int P = blockIdx.x * blockDim.x + threadIdx.x;
-    if (P >= cam.W * cam.H) return;
-    const long long key = keys[P];
-    const unsigned id = (unsigned)(unsigned long long)key;
-    const unsigned f = id - 1u - base;
-    if (id == 0u || f >= nfaces) return; // triangle.py:137-138: sinks are only written where this object is visible
-    bool need_inputs = false, need_view = false;
-    for (int k = 0; k < T.n; k++) {
-        const int kd = T.kind[k];
-        need_inputs |= kd == TINA_SINK_POSITION || kd == TINA_SINK_NORMAL || kd == TINA_SINK_VIEWNORMAL || kd == TINA_SINK_TEXCOORD ||
-                       kd == TINA_SINK_CHESSBOARD || kd == TINA_SINK_VIEWDIR || kd == TINA_SINK_SIMPLE;
-        need_view |= kd == TINA_SINK_VIEWDIR || kd == TINA_SINK_SIMPLE;
-    }
-    ShadeIn in;
-    float px = 0.f, py = 0.f;
-    V3 vd = v3(0.f, 0.f, 0.f);
-    if (need_inputs) pixel_inputs<IDX>(P, f, verts, norms, coors, cam, flags, S, in, px, py);
-    if (need_view) vd = view_direction(cam, px, py);
+// the sinks of one visible pixel: shader.py:21-109, probe.py:21-23 (shared by the triangle and the particle rasteriser)
+__device__ __forceinline__ void write_sinks(const SinkTab &T, int P, long long key, unsigned f, const ShadeIn &in, float px, float py, V3 vd,
+                                            const Cam &cam) {
     for (int k = 0; k < T.n; k++) {
         const int kind = T.kind[k], ncomp = T.ncomp[k];
         const float p0 = T.p[k][0], p1 = T.p[k][1], p2 = T.p[k][2];
@@ -783,7 +762,7 @@ k_gbuffer(const long long *__restrict__ keys, const float *__restrict__ verts, c
         } else if (kind == TINA_SINK_DEPTH) {
             v[0] = v[1] = v[2] = (float)(int)(key >> 32); // shader.py:39-42: engine.depth[P]
         } else if (kind == TINA_SINK_COLOR) {
-            v[0] = v[1] = v[2] = 1.0f; // triangle.py:48
+            v[0] = in.color.x, v[1] = in.color.y, v[2] = in.color.z; // triangle.py:48: (1, 1, 1); particle.py:159: the particle's colour
         } else if (kind == TINA_SINK_POSITION) {
             v[0] = in.pos.x, v[1] = in.pos.y, v[2] = in.pos.z;
         } else if (kind == TINA_SINK_NORMAL) {
@@ -812,4 +791,32 @@ k_gbuffer(const long long *__restrict__ keys, const float *__restrict__ verts, c
             for (int c = 0; c < ncomp; c++) o[c] = v[c];
         }
     }
+}
+
+template <bool IDX>
+__global__ void __launch_bounds__(256)
+k_gbuffer(const long long *__restrict__ keys, const float *__restrict__ verts, const float *__restrict__ norms,
+          const float *__restrict__ coors, const __grid_constant__ Cam cam, uint32_t flags, unsigned base, unsigned nfaces,
+          const __grid_constant__ SinkTab T, const __grid_constant__ Src S) {
+    pdl_wait();
+    const int P = blockIdx.x * blockDim.x + threadIdx.x;
+    if (P >= cam.W * cam.H) return;
+    const long long key = keys[P];
+    const unsigned id = (unsigned)(unsigned long long)key;
+    const unsigned f = id - 1u - base;
+    if (id == 0u || f >= nfaces) return; // triangle.py:137-138: sinks are only written where this object is visible
+    bool need_inputs = false, need_view = false;
+    for (int k = 0; k < T.n; k++) {
+        const int kd = T.kind[k];
+        need_inputs |= kd == TINA_SINK_POSITION || kd == TINA_SINK_NORMAL || kd == TINA_SINK_VIEWNORMAL || kd == TINA_SINK_TEXCOORD ||
+                       kd == TINA_SINK_CHESSBOARD || kd == TINA_SINK_VIEWDIR || kd == TINA_SINK_SIMPLE;
+        need_view |= kd == TINA_SINK_VIEWDIR || kd == TINA_SINK_SIMPLE;
+    }
+    ShadeIn in;
+    in.color = v3(1.0f, 1.0f, 1.0f); // triangle.py:48
+    float px = 0.f, py = 0.f;
+    V3 vd = v3(0.f, 0.f, 0.f);
+    if (need_inputs) pixel_inputs<IDX>(P, f, verts, norms, coors, cam, flags, S, in, px, py);
+    if (need_view) vd = view_direction(cam, px, py);
+    write_sinks(T, P, key, f, in, px, py, vd, cam);
 }

@@ -11,7 +11,7 @@ from .engine import _stream
 from .field import Field
 from .material import material_struct, param_signature
 from .mesh import MAX, _device
-from .shader import Shader, ShaderGroup
+from .shader import Shader, ShaderGroup, _Sink
 
 
 def _dev_f32(arr, shape_tail):
@@ -144,9 +144,20 @@ class ParticleRaster:
         shaders = shader.shaders if isinstance(shader, ShaderGroup) else (shader,)
         flags = (_lib.TINA_COLOR_TONEMAP if tonemap else 0) | (_lib.TINA_COLOR_FILL_BG if fill_bg is not None else 0)
         bg = np.ascontiguousarray(np.broadcast_to(np.asarray(fill_bg if fill_bg is not None else 0, dtype=np.float32), (3,)))
+        # G-buffer shaders of the group (shader.py:21-109, probe.py:21-23): one launch per eight sinks
+        sinks = []
+        for s in shaders:
+            if isinstance(s, _Sink):
+                sinks.append(s)
+            elif hasattr(s, '_sinks'):
+                sinks.extend(s._sinks())
+            elif not isinstance(s, Shader):
+                raise NotImplementedError(f'{type(s).__name__} is not supported by the B200 particle render_color')
+        for i in range(0, len(sinks), _lib.TINA_MAX_SINKS):
+            self._render_sinks(sinks[i:i + _lib.TINA_MAX_SINKS])
         for s in shaders:
             if not isinstance(s, Shader):
-                raise NotImplementedError(f'{type(s).__name__} is not supported by the B200 particle render_color')
+                continue
             t = s.img.to_torch() if hasattr(s.img, 'to_torch') else s.img
             key = id(s.material)
             sig = param_signature(s.material)
@@ -157,6 +168,24 @@ class ParticleRaster:
             mat, keep = hit[1]
             _lib.check(_lib.lib().tina_pars_render_color(self._h, C.byref(mat), s.lighting.struct_ref(), C.c_void_p(t.data_ptr()),
                                                          flags, bg.ctypes.data_as(C.POINTER(C.c_float)), _stream()))
+
+    def _render_sinks(self, sinks):
+        n = len(sinks)
+        npix = self.res[0] * self.res[1]
+        kinds, outs, ncomps, isint = (C.c_int * n)(), (C.c_void_p * n)(), (C.c_int * n)(), (C.c_int * n)()
+        params = np.zeros((n, 3), dtype=np.float32)
+        for i, s in enumerate(sinks):
+            t = s.img.to_torch() if hasattr(s.img, 'to_torch') else s.img
+            if t.dtype not in (torch.float32, torch.int32) or not t.is_contiguous() or not t.is_cuda or t.numel() % npix:
+                raise ValueError('G-buffer image must be a contiguous float32 / int32 CUDA tensor [W, H] or [W, H, n]')
+            if not 1 <= t.numel() // npix <= 3:
+                raise ValueError('G-buffer image must have 1..3 components')
+            kinds[i], outs[i], ncomps[i], isint[i] = s.kind, t.data_ptr(), t.numel() // npix, 1 if t.dtype == torch.int32 else 0
+            p = s.param()
+            if p is not None:
+                params[i] = np.asarray(p, dtype=np.float32).reshape(-1)[:3]
+        _lib.check(_lib.lib().tina_pars_render_gbuffers(self._h, n, kinds, outs, ncomps, isint, params.ctypes.data_as(C.POINTER(C.c_float)),
+                                                        _stream()))
 
     @property
     def occup(self):

@@ -146,9 +146,6 @@ class Scene:
                     opts = {k: v for k, v in self.options.items() if k in ('maxpars', 'coloring', 'clipping')}
                     self.particle_raster = ParticleRaster(self.engine, **opts)
                 raster = self.particle_raster
-                if self.pre_shaders or self.post_shaders:  # (fail here, not in the middle of a frame)
-                    raise NotImplementedError('the B200 particle rasteriser has no G-buffer sinks yet: Scene(ssao=True) and '
-                                              'pre / post shaders cannot be combined with particle objects')
             elif hasattr(object, 'sample_volume'):
                 raise NotImplementedError('the volume rasteriser is outside the B200 raster path')
             else:

@@ -690,6 +690,65 @@ def test_particle_raster_matches_reference_golden(tina):
     assert np.abs(img.to_numpy() - g['image_after0']).max() <= COLOR_TOL
 
 
+def test_particle_gbuffer_sinks_and_screen_space_passes(tina, O):
+    """ParticleRaster.render_color serves every shader of a ShaderGroup (particle.py:129-161): the normal / position /
+    colour / id sinks of the visible sphere points against the oracle, and Scene(ssao=True) / Scene(ssr=True) with particle
+    objects (the AO and SSR fields equal the oracle's on this pipeline's own buffers)."""
+    import os
+    import torch
+    from test_golden import GOLDEN
+    g = np.load(os.path.join(GOLDEN, 'particles_and_mesh.npz'))
+    W, H = (int(v) for v in g['res'])
+    engine = tina.Engine((W, H))
+    engine.W2V[None], engine.V2W[None], engine.bias[None] = g['W2V'], g['V2W'], g['bias']
+    pr = tina.ParticleRaster(engine)
+    pr.set_particles(g['pos'])
+    pr.set_particle_radii(g['rad'])
+    pr.set_particle_colors(g['col'])
+    engine.clear_depth()
+    pr.render_occup()
+    f3 = lambda: tina.Field(torch.zeros((W, H, 3), device='cuda'))  # noqa: E731
+    nrm, pos, col = f3(), f3(), f3()
+    ids = tina.Field(torch.full((W, H), -1, dtype=torch.int32, device='cuda'))
+    probe = tina.ProbeShader((W, H))
+    group = tina.ShaderGroup([tina.NormalShader(nrm), tina.PositionShader(pos), tina.ColorShader(col), tina.ConstShader(ids, 7), probe])
+    pr.render_color(group)
+    torch.cuda.synchronize()
+    occ = pr.occup.to_numpy()
+    assert np.array_equal(occ, g['occup0']) and (occ >= 0).sum() > 50
+    rpos, rnrm = O.pars_attrs(g['pos'], g['rad'], occ, g['W2V'], g['V2W'], W, H, bias=g['bias'])
+    assert np.abs(nrm.to_numpy() - rnrm).max() <= 2e-6 and np.abs(pos.to_numpy() - rpos).max() <= 2e-6
+    vis = occ >= 0
+    assert np.array_equal(col.to_numpy()[vis], g['col'][occ[vis]]) and not col.to_numpy()[~vis].any()
+    assert np.array_equal(ids.to_numpy() == 7, vis)
+    assert np.array_equal(probe.elmid.to_numpy()[vis], occ[vis])
+    # screen-space passes over particles + a mesh
+    for opts in (dict(ssao=True), dict(ssr=True)):
+        scene = tina.Scene((W, H), smoothing=True, tonemap=False, **opts)
+        pars = tina.SimpleParticles(maxpars=64)
+        pars.set_particles(g['pos'])
+        pars.set_particle_radii(g['rad'])
+        mats = [tina.PBR(metallic=0.8, roughness=0.2), tina.Diffuse(color=[0.3, 0.5, 0.9])]
+        scene.add_object(pars, mats[0])
+        scene.add_object(tina.MeshModel(scenes.load_monkey()), mats[1])
+        scene.engine.W2V[None], scene.engine.V2W[None] = g['W2V'], g['V2W']
+        scene.triangle_raster.set_tuning(fast_shading=0)
+        if 'ssr' in opts:
+            scene.ssr.nsamples[None], scene.ssr.nsteps[None] = 6, 16
+        scene.render()
+        torch.cuda.synchronize()
+        depth, nb = scene.engine.depth.to_numpy(), scene.norm_buffer.to_numpy()
+        po = scene.particle_raster.occup.to_numpy()
+        assert (np.square(nb[po >= 0]).sum(-1) > 0.99).all() and (po >= 0).sum() > 50  # the particles wrote their normals
+        if 'ssao' in opts:
+            ao_ref = O.ssao_render(depth, nb, g['W2V'], g['V2W'], scene.ssao.samples.cpu().numpy(), scene.ssao.rotations.cpu().numpy())
+            ao = scene.ssao.img.to_numpy()
+            assert np.abs(ao - ao_ref).max() <= 1e-6 and (ao != ao_ref).mean() < 0.01 and ao_ref.max() > 0.2
+        else:
+            assert set(np.unique(scene.mtlid_buffer.to_numpy()[po >= 0]).tolist()) == {0}
+            assert float(scene.ssr.img.to_numpy()[..., 3].max()) > 0
+
+
 def test_wireframe_raster_matches_reference_golden(tina, O):
     """§8f row 3: WireframeRaster + MeshToWire through tina.Scene over a solid mesh, against the golden produced
     by the reference's own sources; plus long / off-screen / degenerate lines against the oracle."""
