@@ -28,7 +28,10 @@ for rep in range(2):
         for i in range(24): steps[i % ns]()
         torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        import time
         a.record()
+        t0 = time.perf_counter()
         for i in range(K): steps[i % ns]()
+        host = (time.perf_counter() - t0) / K * 1e6
         b.record(); torch.cuda.synchronize()
-        print(f'{ns} scenes in rotation ({ns * 100} MB touched per cycle): {a.elapsed_time(b) / K * 1e3:.2f} us / step', flush=True)
+        print(f'{ns} scenes in rotation ({ns * 100} MB touched per cycle): {a.elapsed_time(b) / K * 1e3:.2f} us / step (host enqueue {host:.1f} us / step)', flush=True)
