@@ -573,7 +573,9 @@ def run_ours(args):
                 rs.render_color(sh, fill_bg=bg)
             return sc, st
         pool = [make_step(k) for k in range(ROTATE_SCENES)]
-        for i in range(max(3, args.warmup) * ROTATE_SCENES):
+        # (every scene is warmed at least 10 times: its rasteriser stops launching the idle tile-path kernel after 8 frames
+        # that queued no large face, as it has in any render loop)
+        for i in range(max(10, args.warmup) * ROTATE_SCENES):
             pool[i % ROTATE_SCENES][1]()
         barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
