@@ -279,7 +279,9 @@ int tina_raster_buffers(TinaRaster *r, const float **verts, const float **norms,
  *      0 = one face per thread like every other indexed source,
  * 18 = indexed sources: when no set_faces* call happened since the previous render_occup, the vertex-stage blocks of this
  *      one do not wait for the previous render_color (they write the other of two per-vertex record sets; the blocks that
- *      clear the keys still wait), so consecutive frames overlap by that kernel's last wave (default 1) */
+ *      clear the keys still wait), so consecutive frames overlap by that kernel's last wave (default 1),
+ * 19 = render_color passes without frame glue / composite run as a smaller grid that walks the 256-pixel chunks with a
+ *      grid stride: value / 4 chunks per CTA, at least five CTAs per SM (default 15 = 3.75 chunks; 0 = one CTA per chunk) */
 int tina_raster_set_tuning(TinaRaster *r, int which, int value);
 /* counters of the last render_occup (synchronises): faces culled, clipped, per-thread,
  * per-warp, queued for the tile path, tile-list entries */

@@ -588,8 +588,11 @@ struct PeerTab {
 // plain ones compile those paths away (carrying them as run-time options cost the C2 frame 2 us).
 // COMP: the sort-last composite over peer memory (keys = MIN over every rank's buffer, image strip stored into the
 // root rank's image): its own instantiations, so that the plain kernels carry none of it.
-template <int KIND, bool IDX, bool FAST, int LEAN = 0, bool GLUE = false, bool COMP = false>
-__global__ void __launch_bounds__(K4_THREADS, K4_MINBLOCKS)
+// PERSIST: a smaller grid walks the chunks with a grid stride (~3.75 chunks per CTA) instead of one CTA per chunk: a
+// quarter of the CTA launches (launching the 8100 CTAs of a 1080p pass costs 4 us by itself, tools/micro/cta_turnover.cu),
+// and the last CTA starts -- and lets the next frame's vertex stage go -- earlier.  C2 sustained frame 49.9 -> 48.0 us.
+template <int KIND, bool IDX, bool FAST, int LEAN = 0, bool GLUE = false, bool COMP = false, bool PERSIST = false>
+__global__ void __launch_bounds__(K4_THREADS, (PERSIST && LEAN != 0) ? 5 : K4_MINBLOCKS) // (lean + PERSIST: 48 registers = five CTAs per SM like the plain form)
 k_render_color(const long long *__restrict__ keys, const float *__restrict__ verts, const float *__restrict__ norms,
                const float *__restrict__ coors, const __grid_constant__ Cam cam, uint32_t flags, unsigned base,
                unsigned nfaces, const __grid_constant__ TinaMaterial mat, const __grid_constant__ TinaLighting L,
@@ -642,7 +645,8 @@ k_render_color(const long long *__restrict__ keys, const float *__restrict__ ver
     };
     // (CTAs take the chunks in plain order: spreading covered and background chunks over the launch -- CTA b -> chunk
     // (b % 8) * n / 8 + b / 8 -- measured 1.3 us slower on C2, profiles/r2_k4_variants.md)
-    const long long p0 = (long long)pix_lo + (long long)blockIdx.x * K4_THREADS;
+    static_assert(!(PERSIST && (COMP || GLUE)), "the persistent form serves the plain passes only");
+    auto shade_chunk = [&](const long long p0) {
     // flagval != 0: this object's render_occup was the engine's last, its flags carry its own stamp -> a chunk with
     // any other value holds none of its pixels.  flagval == 0: only "nothing rasterised here since the clear" is known.
     const unsigned char cf = blkflags ? blkflags[p0 >> FLAG_SHIFT] : (unsigned char)1;
@@ -732,6 +736,13 @@ k_render_color(const long long *__restrict__ keys, const float *__restrict__ ver
     if (cflags & TINA_COLOR_TONEMAP) c.x = aces_t<FAST>(c.x), c.y = aces_t<FAST>(c.y), c.z = aces_t<FAST>(c.z);
     __stcs(out, c.x), __stcs(out + 1, c.y), __stcs(out + 2, c.z);
     if (acc) accumulate(P, c.x, c.y, c.z);
+    };
+    if (!PERSIST) {
+        shade_chunk((long long)pix_lo + (long long)blockIdx.x * K4_THREADS);
+    } else {
+        const unsigned nch = ((unsigned)(pix_hi - pix_lo) + K4_THREADS - 1u) / K4_THREADS;
+        for (unsigned c = blockIdx.x; c < nch; c += gridDim.x) shade_chunk((long long)pix_lo + (long long)c * K4_THREADS);
+    }
 }
 
 // G-buffer sinks (core/shader.py:21-109, probe.py:21-23): attributes of the visible surface per pixel.  One launch

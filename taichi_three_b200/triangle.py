@@ -311,7 +311,7 @@ class TriangleRaster:
 
     def set_tuning(self, tiny_max=None, force_tiles=None, collect_stats=None, profile=None, tighten=None,
                    precheck=None, scan_max=None, generic_vm=None, balance=None, pdl=None, indexed=None, adaptive=None,
-                   fast_shading=None, lean_kernels=None, force_general=None, grid_tiles=None, grid_quads=None, overlap_vertex=None):
+                   fast_shading=None, lean_kernels=None, force_general=None, grid_tiles=None, grid_quads=None, overlap_vertex=None, persist_k4=None):
         """Strategy knobs (every setting produces identical ids/depth bits; only fast_shading changes colour, by
         < 1e-4): tiny_max = most candidate pixels a
         face may have to be rasterised per thread in the setup kernel (more -> tile path);
@@ -328,7 +328,9 @@ class TriangleRaster:
         grid_tiles = plain square MeshGrid: persistent warps over cp.async-staged row chunks (default 0: slower);
         grid_quads = plain square MeshGrid: one quad (two faces) per thread (default 1; 0 = one face per thread);
         overlap_vertex = when no set_object happened since the previous render_occup, the vertex stage of this one starts
-        while the previous render_color is still in its last wave (default 1; it writes the other of two record sets)."""
+        while the previous render_color is still in its last wave (default 1; it writes the other of two record sets);
+        persist_k4 = render_color passes without frame glue / composite run as a smaller grid walking the 256-pixel chunks
+        with a grid stride, persist_k4 / 4 chunks per CTA (default 15 = 3.75; 0 = one CTA per chunk)."""
         L = _lib.lib()
         if tiny_max is not None:
             _lib.check(L.tina_raster_set_tuning(self._h, 0, int(tiny_max)))
@@ -339,7 +341,7 @@ class TriangleRaster:
         if profile is not None:
             _lib.check(L.tina_raster_set_tuning(self._h, 4, int(profile)))
         for which, v in ((5, tighten), (6, precheck), (7, scan_max), (8, generic_vm), (9, balance), (10, pdl), (11, indexed), (12, adaptive),
-                         (13, fast_shading), (14, lean_kernels), (15, force_general), (16, grid_tiles), (17, grid_quads), (18, overlap_vertex)):
+                         (13, fast_shading), (14, lean_kernels), (15, force_general), (16, grid_tiles), (17, grid_quads), (18, overlap_vertex), (19, persist_k4)):
             if v is not None:
                 _lib.check(L.tina_raster_set_tuning(self._h, which, int(v)))
 

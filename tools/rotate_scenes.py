@@ -15,6 +15,7 @@ def make(k):
     scene.engine.set_camera(*scenes.default_camera(W / H))
     raster, shader = scene.triangle_raster, scene.shaders[id(mat)]
     raster.set_object(mesh)
+    if os.environ.get('TINA_PERSIST') is not None: raster.set_tuning(persist_k4=int(os.environ['TINA_PERSIST']))
     if os.environ.get('TINA_OVERLAP') is not None: raster.set_tuning(overlap_vertex=int(os.environ['TINA_OVERLAP']))
     def step():
         scene.engine.clear_depth(); raster.render_occup(); raster.render_color(shader, fill_bg=bg)
