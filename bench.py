@@ -40,7 +40,7 @@ sys.path.insert(0, os.path.join(ROOT, 'tests'))
 
 import numpy as np  # noqa: E402
 
-K1_NCU = 'r2_v5_k_raster_quads_ncu.txt'
+K1_NCU = 'r2_v6_k_raster_quads_ncu.txt'
 
 
 def ncu_traffic(kernel_file=K1_NCU):
