@@ -412,6 +412,50 @@ def case_ssr():
         sorted(set(out['mtlid'][hit].tolist())), os.path.getsize(path)))
 
 
+def case_ssr_defaults():
+    """postp/ssr.py with its DEFAULT parameters (32 samples x 32 steps, stepsize 2, tolerance 15, blurring 4; ssr.py:20-28)
+    in a Scene without texturing (the dummy (1, 1) texcoord field of scene/raster.py:63-64): Diffuse floor, metallic PBR
+    monkey, at 32 x 24 so that the serial Python run stays around two minutes."""
+    ns = {n: getattr(tina, n) for n in ('PBR', 'Classic', 'Diffuse', 'Lamp', 'Lambert', 'Phong', 'Emission', 'CookTorrance', 'Texture',
+                                        'FresnelFactor', 'MixMaterial', 'ScaleMaterial', 'AddMaterial')}
+    specs = ['PBR(basecolor=[0.9, 0.7, 0.5], metallic=0.9, roughness=0.1)', 'Diffuse(color=[0.4, 0.6, 0.8])']
+    W, H = 32, 24
+    scene = tina.Scene((W, H), smoothing=True, ssr=True, tonemap=False)
+    mats = [eval(sp, dict(ns)) for sp in specs]
+    scene.add_object(tina.MeshModel(os.path.join(REF, 'assets/monkey.obj')), mats[0])
+    floor = tina.MeshTransform(tina.MeshModel(os.path.join(REF, 'assets/plane.obj')), tina.translate([0, -0.9, 0]) @ tina.scale(2.5))
+    scene.add_object(floor, mats[1])
+    camera(scene, W / H, back=(0.2, 0.9, 3.0))
+    scene.mtltab.clear_materials()
+    for m in scene.materials:
+        scene.mtltab.add_material(m)
+    eng = scene.engine
+    scene.image.fill(scene.bgcolor)
+    eng.clear_depth()
+    for sh in scene.pre_shaders + scene.post_shaders:
+        sh.clear_buffer()
+    for obj, oinfo in scene.objects.items():
+        oinfo.raster.set_object(obj)
+        oinfo.raster.render_occup()
+        oinfo.raster.render_color(scene.shaders[oinfo.material])
+    out = {'W2V': eng.W2V.to_numpy().astype(np.float32), 'V2W': eng.V2W.to_numpy().astype(np.float32),
+           'depth': eng.depth.to_numpy().astype(np.int32), 'normals': scene.norm_buffer.to_numpy().astype(np.float32),
+           'mtlid': scene.mtlid_buffer.to_numpy().astype(np.int32), 'image_before': scene.image.to_numpy().astype(np.float32),
+           'nspecs': np.int32(len(specs)), 'nsamples': np.int32(scene.ssr.nsamples[None]), 'nsteps': np.int32(scene.ssr.nsteps[None]),
+           'stepsize': np.float32(scene.ssr.stepsize[None]), 'tolerance': np.float32(scene.ssr.tolerance[None]),
+           'blurring': np.int32(scene.ssr.blurring[None])}
+    for i, sp in enumerate(specs):
+        out[f'spec{i}'] = np.array(sp)
+    scene.ssr.render(eng, scene.image)
+    out['ssr'] = scene.ssr.img.to_numpy().astype(np.float32)
+    scene.ssr.apply(scene.image)
+    out['image_after'] = scene.image.to_numpy().astype(np.float32)
+    path = os.path.join(HERE, 'particles_ssr_defaults.npz')
+    np.savez_compressed(path, **out)
+    print('particles_ssr_defaults: %d px with hits, mean alpha %.4f, %d B' % (int((out['ssr'][..., 3] > 0).sum()),
+                                                                              float(out['ssr'][..., 3].mean()), os.path.getsize(path)))
+
+
 def case_micro():
     """The C2 regime at golden size: sub-pixel faces.  (a) MeshGrid(56) wave on a 40x30 screen (~0.3 px per face,
     smooth normals, Classic) -- most faces cover no sample, many samples lie within 1e-2 px of an edge;
@@ -540,6 +584,7 @@ if __name__ == '__main__':
     case_micro()
     case_ssao()
     case_ssr()
+    case_ssr_defaults()
     case_monkey()
     case_grid()
     case_cornell()

@@ -249,6 +249,18 @@ def test_oracle_ssr_matches_reference_sources(tina, O):
     assert np.array_equal(O.ssr_apply(g['image_before'], g['ssr'], int(g['blurring'])), g['image_after'])
 
 
+def test_oracle_ssr_default_parameters_match_reference_sources(tina, O):
+    """The same with SSR's default parameters (32 samples x 32 steps, ssr.py:20-28) in a scene without texturing (texcoord 0)."""
+    g = np.load(os.path.join(GOLDEN, 'particles_ssr_defaults.npz'))
+    assert (int(g['nsamples']), int(g['nsteps']), int(g['blurring'])) == (32, 32, 4)
+    mats = [_material(tina, g, i, 'spec') for i in range(int(g['nspecs']))]
+    img4 = O.ssr_render(g['depth'], g['normals'], None, g['mtlid'], mats, g['image_before'], g['W2V'], g['V2W'],
+                        nsamples=32, nsteps=32, stepsize=float(g['stepsize']), tolerance=float(g['tolerance']), blurring=4)
+    assert (g['ssr'][..., 3] > 0).sum() > 200
+    assert np.abs(img4 - g['ssr']).max() <= 2e-6
+    assert np.array_equal(O.ssr_apply(g['image_before'], g['ssr'], 4), g['image_after'])
+
+
 def test_oracle_ssao_matches_reference_sources(tina, O):
     """postp/ssao.py run from the reference's own sources under the shim (golden: depth, normal G-buffer, the sample /
     rotation tables it drew, the AO field, the image before and after apply) against the oracle restatement."""
