@@ -1157,6 +1157,31 @@ def test_ssr_matches_reference_golden_and_scene_option(tina, O):
     assert np.abs(after - O.ssr_apply(before, scene.ssr.img.to_numpy())).max() <= 1e-6
 
 
+def test_ssr_default_parameters_match_reference_golden(tina):
+    """SSR with its default 32 samples x 32 steps, scene without texturing (texcoord 0), against the reference's own run."""
+    import os
+    import torch
+    from test_golden import GOLDEN, _material
+    from taichi_three_b200.scene import MaterialTable
+    g = np.load(os.path.join(GOLDEN, 'particles_ssr_defaults.npz'))
+    W, H = g['depth'].shape
+    eng = tina.Engine((W, H))
+    eng.W2V[None], eng.V2W[None] = g['W2V'], g['V2W']
+    eng.keys.copy_(torch.as_tensor(g['depth'].astype(np.int64) << 32).cuda())
+    tab = MaterialTable()
+    for i in range(int(g['nspecs'])):
+        tab.add_material(_material(tina, g, i, 'spec'))
+    ssr = tina.SSR((W, H), tina.Field(torch.as_tensor(g['normals']).cuda()), None, tina.Field(torch.as_tensor(g['mtlid']).cuda()), tab)
+    assert (int(ssr.nsamples[None]), int(ssr.nsteps[None]), int(ssr.blurring[None])) == (32, 32, 4)
+    img = tina.Field(torch.as_tensor(g['image_before']).cuda())
+    ssr.render(eng, img)
+    torch.cuda.synchronize()
+    ok, frac, err = _ssr_close(ssr.img.to_numpy(), g['ssr'])
+    assert ok and err <= 2e-5, (frac, err)
+    ssr.apply(img)
+    assert np.abs(img.to_numpy() - g['image_after']).max() <= 1e-3 and np.abs(img.to_numpy() - g['image_after']).mean() <= 1e-5
+
+
 def test_ssao_and_ssr_taa_modes_follow_the_hash_stream(tina, O):
     """taa=True: fresh samples per pixel and frame (ssao.py:52-56,80-81; ssr.py:72).  The reference's ti.random() stream
     is unspecified; the product draws from the Wang hash seeded with (pixel, frame) and the oracle restates that stream:
