@@ -1182,6 +1182,33 @@ def test_ssr_default_parameters_match_reference_golden(tina):
     assert np.abs(img.to_numpy() - g['image_after']).max() <= 1e-3 and np.abs(img.to_numpy() - g['image_after']).mean() <= 1e-5
 
 
+def test_reference_ssr_script_flow(tina):
+    """The reference's own tests/ssr.py without its GUI: Scene(ssr=True, taa=True), PBR materials driven by tina.Param,
+    a transformed MeshGrid as the mirror plane, the SSR fields set every frame, TAA accumulation over a few frames."""
+    import torch
+    scene = tina.Scene((160, 120), smoothing=True, ssr=True, taa=True)
+    monkey = tina.MeshModel(scenes.load_monkey())
+    scene.add_object(monkey, tina.PBR(metallic=0.0, roughness=0.4))
+    param_metallic, param_roughness = tina.Param(), tina.Param()
+    plane = tina.MeshTransform(tina.MeshGrid(32), tina.translate([0, -1, 0]) @ tina.scale(2) @ tina.eularXYZ([-np.pi / 2, 0, 0]))
+    scene.add_object(plane, tina.PBR(metallic=param_metallic, roughness=param_roughness))
+    scene.engine.set_camera(*tina.orbit_camera(radius=3.5, theta=0.45, phi=0.3, aspect=160 / 120))
+    imgs = []
+    for metallic in (1.0, 0.0):
+        scene.clear()
+        for frame in range(3):
+            scene.ssr.nsteps[None], scene.ssr.nsamples[None], scene.ssr.blurring[None] = 64, 12, 4
+            scene.ssr.stepsize[None], scene.ssr.tolerance[None] = 2, 15
+            param_metallic.value[None], param_roughness.value[None] = metallic, 0.0
+            scene.render()
+        torch.cuda.synchronize()
+        img = scene.img.to_numpy()
+        assert np.isfinite(img).all() and img.max() > 0.1
+        assert float(scene.ssr.img.to_numpy()[..., 3].max()) > 0 and scene.accum.count[0] == 3
+        imgs.append(img)
+    assert np.abs(imgs[0] - imgs[1]).max() > 1e-3  # the mirror plane reflects, the dielectric one much less
+
+
 def test_ssao_and_ssr_taa_modes_follow_the_hash_stream(tina, O):
     """taa=True: fresh samples per pixel and frame (ssao.py:52-56,80-81; ssr.py:72).  The reference's ti.random() stream
     is unspecified; the product draws from the Wang hash seeded with (pixel, frame) and the oracle restates that stream:
