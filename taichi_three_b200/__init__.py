@@ -13,7 +13,7 @@ from .assimp import readobj, readgltf, objverts, objnorms, objcoors, objorient, 
 from .lighting import Lighting
 from .shader import (IShader, Shader, ShaderGroup, ConstShader, PositionShader, DepthShader, NormalShader,
                      ViewNormalShader, TexcoordShader, ColorShader, ChessboardShader, ViewdirShader, SimpleShader, ProbeShader)
-from .mesh import (MAX, SimpleMesh, MeshModel, MeshGrid, MeshTransform, MeshFlipCulling, MeshNoCulling,
+from .mesh import (MAX, SimpleMesh, PrimitiveMesh, ConnectiveMesh, MeshModel, MeshGrid, MeshTransform, MeshFlipCulling, MeshNoCulling,
                    MeshFlipNormal, MeshFlatNormal, MeshSmoothNormal, MeshEditBase)
 from .engine import Engine
 from .triangle import TriangleRaster

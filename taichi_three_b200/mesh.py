@@ -102,6 +102,127 @@ class SimpleMesh:
         return FaceSource('simple', verts=self._verts, norms=self._norms, coors=self._coors, nfaces=self.get_nfaces())
 
 
+def primitive_sphere(lons=32, lats=24, rad=1):
+    """mesh/prim.py:21-48 as arrays: float32 [nfaces, 3 corners, 3 (vertex, normal, texcoord), 3].  A lat / lon grid of
+    (lats + 1) x (lons + 1) points; cell (lat, lon) gives the triangles (p00, p01, p11) unless lat == 0 and (p11, p10, p00)
+    unless lat == lats - 1, in that order.  float64 arithmetic, rounded to float32 at the end, like the reference."""
+    la, lo = np.meshgrid(np.arange(lats + 1, dtype=np.float64) / lats, np.arange(lons + 1, dtype=np.float64) / lons, indexing='ij')
+    a, o = (la - 0.5) * np.pi, (lo * 2 - 1) * np.pi
+    nrm = np.stack([np.cos(a) * np.cos(o), np.cos(a) * np.sin(o), np.sin(a)], axis=-1)
+    pts = np.stack([nrm * rad, nrm, np.stack([lo, la, np.zeros_like(la)], axis=-1)], axis=-2)  # [lat, lon, 3 attrs, 3]
+    return _quad_cells(pts, lats, lons, skip_first_row_upper=True, skip_last_row_lower=True)
+
+
+def _quad_cells(pts, lats, lons, skip_first_row_upper=False, skip_last_row_lower=False):
+    p00, p01, p11, p10 = pts[:-1, :-1], pts[:-1, 1:], pts[1:, 1:], pts[1:, :-1]
+    upper = np.stack([p00, p01, p11], axis=2)  # [lats, lons, 3 corners, 3 attrs, 3]
+    lower = np.stack([p11, p10, p00], axis=2)
+    both = np.stack([upper, lower], axis=2).reshape(lats * lons * 2, 3, 3, 3)
+    keep = np.ones((lats, lons, 2), dtype=bool)
+    if skip_first_row_upper:
+        keep[0, :, 0] = False
+    if skip_last_row_lower:
+        keep[lats - 1, :, 1] = False
+    return np.ascontiguousarray(both[keep.reshape(-1)], dtype=np.float32)
+
+
+def primitive_cylinder(lons=32, lats=4, rad=1, hei=2):
+    """mesh/prim.py:50-87: the side as (lats x lons) quad cells, then the bottom fan (p[0, lon + 1], p[0, lon], centre) with
+    normal (0, 0, -1) and the top fan (centre, p[lats, lon], p[lats, lon + 1]) with normal (0, 0, 1); the caps carry their
+    normal as the texture coordinate too (sic)."""
+    la, lo = np.meshgrid(np.arange(lats + 1, dtype=np.float64) / lats, np.arange(lons + 1, dtype=np.float64) / lons, indexing='ij')
+    o = (lo * 2 - 1) * np.pi
+    x, y, z = np.cos(o), np.sin(o), la - 0.5
+    pts = np.stack([np.stack([x * rad, y * rad, z * hei], -1), np.stack([x, y, np.zeros_like(x)], -1),
+                    np.stack([lo, la, np.zeros_like(la)], -1)], axis=-2)
+    side = _quad_cells(pts, lats, lons)
+
+    def fan(row, zc, nz, centre_first):
+        n = np.array([0.0, 0.0, nz])
+        ring = pts[row, :, 0]  # [lons + 1, 3] positions
+        centre = np.broadcast_to(np.array([0.0, 0.0, zc]), (lons, 3))
+        corners = [centre, ring[:-1], ring[1:]] if centre_first else [ring[1:], ring[:-1], centre]
+        tri = np.stack(corners, axis=1)  # [lons, 3 corners, 3]
+        attr = np.broadcast_to(n, tri.shape)
+        return np.stack([tri, attr, attr], axis=2)
+    return np.ascontiguousarray(np.concatenate([side, fan(0, -hei / 2, -1.0, False), fan(lats, hei / 2, 1.0, True)]), dtype=np.float32)
+
+
+class PrimitiveMesh(SimpleMesh):
+    """mesh/prim.py:5-101: a SimpleMesh filled from `faces` [N, 3 corners, 3 (vertex, normal, texcoord), 3]."""
+
+    def __init__(self, faces):
+        faces = np.asarray(faces, dtype=np.float32)
+        if faces.ndim != 4 or faces.shape[1:] != (3, 3, 3):
+            raise ValueError(f'PrimitiveMesh takes [N, 3, 3, 3] faces (vertex, normal, texcoord per corner), got {faces.shape}')
+        super().__init__(maxfaces=len(faces), npolygon=3)
+        self.set_face_verts(np.ascontiguousarray(faces[:, :, 0]))
+        self.set_face_norms(np.ascontiguousarray(faces[:, :, 1]))
+        self.set_face_coors(np.ascontiguousarray(faces[:, :, 2]))
+
+    @classmethod
+    def sphere(cls, lons=32, lats=24, rad=1):
+        return cls(primitive_sphere(lons, lats, rad))
+
+    @classmethod
+    def cylinder(cls, lons=32, lats=4, rad=1, hei=2):
+        return cls(primitive_cylinder(lons, lats, rad, hei))
+
+    @classmethod
+    def asset(cls, name):
+        """prim.py:89-101 (quirk kept: the per-corner triples are built as (vertex, texcoord + [0], normal), so the constructor
+        reads the texture coordinates as normals and the normals as texture coordinates)."""
+        from .assimp import readobj
+        obj = readobj('assets/' + name + '.obj', quadok=True)
+        f = obj['f']
+        if f.shape[1] != 3:
+            raise NotImplementedError('only triangle assets are on the B200 raster path')
+        verts, coors, norms = obj['v'][f[:, :, 0]], obj['vt'][f[:, :, 1]], obj['vn'][f[:, :, 2]]
+        coors3 = np.concatenate([coors, np.zeros(coors.shape[:2] + (1,), coors.dtype)], axis=-1)
+        return cls(np.stack([verts, coors3, norms], axis=2))
+
+
+class ConnectiveMesh:
+    """mesh/conn.py:5-103: vertices, normals and texture coordinates per VERTEX, faces as vertex-index triples."""
+
+    def __init__(self, maxfaces=MAX, maxverts=MAX, npolygon=3):
+        if npolygon != 3:
+            raise NotImplementedError('only triangle meshes (npolygon=3) are on the B200 raster path')
+        self.maxfaces, self.maxverts, self.npolygon = maxfaces, maxverts, npolygon
+        self._v = np.zeros((0, 3), np.float32)
+        self._vn = self._vt = None
+        self._f = np.zeros((0, 3), np.int32)
+        self._model = None
+
+    def get_npolygon(self):
+        return self.npolygon
+
+    def get_nfaces(self):
+        return len(self._f)
+
+    def set_vertices(self, verts):  # conn.py:71-76
+        self._v, self._model = np.ascontiguousarray(np.asarray(verts, np.float32)[:self.maxverts, :3]), None
+
+    def set_vert_norms(self, norms):  # conn.py:78-83
+        self._vn, self._model = np.ascontiguousarray(np.asarray(norms, np.float32)[:self.maxverts, :3]), None
+
+    def set_vert_coors(self, coors):  # conn.py:85-90
+        self._vt, self._model = np.ascontiguousarray(np.asarray(coors, np.float32)[:self.maxverts, :2]), None
+
+    def set_faces(self, faces):  # conn.py:92-97
+        self._f, self._model = np.ascontiguousarray(np.asarray(faces, np.int32)[:self.maxfaces, :3]), None
+
+    def _source(self):
+        if self._model is None:
+            n = len(self._v)
+            vn = self._vn if self._vn is not None else np.zeros((n, 3), np.float32)
+            vt = self._vt if self._vt is not None else np.zeros((n, 2), np.float32)
+            if len(vn) < n or len(vt) < n:
+                raise ValueError('ConnectiveMesh: normals / texture coordinates must cover every vertex')
+            self._model = MeshModel({'v': self._v, 'vn': vn, 'vt': vt, 'f': np.repeat(self._f[:, :, None], 3, axis=2)})
+        return self._model._source()
+
+
 class MeshModel:
     """mesh/model.py:5-73: indexed mesh from an OBJ dict {'v','vt','vn','f'} or a path."""
 

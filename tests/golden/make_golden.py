@@ -456,6 +456,25 @@ def case_ssr_defaults():
                                                                               float(out['ssr'][..., 3].mean()), os.path.getsize(path)))
 
 
+def case_prims():
+    """mesh/prim.py:21-87: the face lists PrimitiveMesh.sphere / .cylinder build (vertex, normal, texcoord per corner),
+    captured from the reference's own generator before they reach its Taichi fields."""
+    import importlib
+    prim = importlib.import_module('tina.mesh.prim')
+
+    class Capture:
+        def __new__(cls, faces):
+            return np.array(faces, dtype=np.float32)
+    out = {}
+    for name, args in (('sphere_8_6', (8, 6, 1)), ('sphere_5_3', (5, 3, 0.7)), ('sphere_default', ())):
+        out[name] = prim.PrimitiveMesh.sphere.__func__(Capture, *args)
+    for name, args in (('cylinder_8_2', (8, 2, 1, 2)), ('cylinder_5_3', (5, 3, 0.6, 1.5)), ('cylinder_default', ())):
+        out[name] = prim.PrimitiveMesh.cylinder.__func__(Capture, *args)
+    path = os.path.join(HERE, 'particles_prims.npz')  # (particles_ prefix = not a rendered raster scene, see test_golden.CASES)
+    np.savez_compressed(path, **out)
+    print('particles_prims:', {k: v.shape for k, v in out.items()}, os.path.getsize(path), 'B')
+
+
 def case_micro():
     """The C2 regime at golden size: sub-pixel faces.  (a) MeshGrid(56) wave on a 40x30 screen (~0.3 px per face,
     smooth normals, Classic) -- most faces cover no sample, many samples lie within 1e-2 px of an edge;
@@ -585,6 +604,7 @@ if __name__ == '__main__':
     case_ssao()
     case_ssr()
     case_ssr_defaults()
+    case_prims()
     case_monkey()
     case_grid()
     case_cornell()

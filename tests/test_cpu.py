@@ -329,6 +329,17 @@ def test_sample_trees_of_product_and_oracle_agree(O, tina):
         sample_struct(object(), torch.device('cpu'))
 
 
+def test_primitive_mesh_generators_match_reference_golden():
+    """mesh/prim.py: PrimitiveMesh.sphere / .cylinder face lists (vertex, normal, texcoord per corner) equal the reference's
+    own generator bit for bit (golden: make_golden.py::case_prims)."""
+    from taichi_three_b200.mesh import primitive_sphere, primitive_cylinder
+    g = np.load(os.path.join(ROOT, 'tests', 'golden', 'particles_prims.npz'))
+    assert np.array_equal(primitive_sphere(8, 6, 1), g['sphere_8_6']) and np.array_equal(primitive_sphere(5, 3, 0.7), g['sphere_5_3'])
+    assert np.array_equal(primitive_sphere(), g['sphere_default']) and g['sphere_default'].shape == (1472, 3, 3, 3)
+    assert np.array_equal(primitive_cylinder(8, 2, 1, 2), g['cylinder_8_2']) and np.array_equal(primitive_cylinder(5, 3, 0.6, 1.5), g['cylinder_5_3'])
+    assert np.array_equal(primitive_cylinder(), g['cylinder_default']) and g['cylinder_default'].shape == (320, 3, 3, 3)
+
+
 def test_bench_reference_arm_is_product_free_and_uses_every_core():
     """`bench.py --impl reference` under torchrun's OMP_NUM_THREADS=1: every host core, the same config object as the
     GPU arm, and no product module (nor libtina_b200.so) in the process."""

@@ -1182,6 +1182,49 @@ def test_ssr_default_parameters_match_reference_golden(tina):
     assert np.abs(img.to_numpy() - g['image_after']).max() <= 1e-3 and np.abs(img.to_numpy() - g['image_after']).mean() <= 1e-5
 
 
+def test_primitive_and_connective_meshes(tina, O):
+    """mesh/prim.py + mesh/conn.py through the raster: a PrimitiveMesh sphere + cylinder scene against the oracle on the same
+    face arrays (docs/primitives.py's objects), and a ConnectiveMesh equal to the MeshModel with the same shared indices."""
+    import torch
+    from taichi_three_b200.mesh import primitive_sphere, primitive_cylinder
+    W, H = 160, 120
+    view, proj = scenes.default_camera(W / H)
+    scene = tina.Scene((W, H), smoothing=True, texturing=True)
+    sph, cyl = tina.PrimitiveMesh.sphere(16, 12, 0.8), tina.MeshTransform(tina.PrimitiveMesh.cylinder(12, 2, 0.4, 1.2), tina.translate([1.1, 0, 0]))
+    scene.add_object(sph, tina.Classic())
+    scene.add_object(cyl, tina.Diffuse(color=[0.8, 0.5, 0.3]))
+    scene.engine.set_camera(view, proj)
+    scene.triangle_raster.set_tuning(fast_shading=0)
+    scene.render()
+    torch.cuda.synchronize()
+    fs, fc = primitive_sphere(16, 12, 0.8), primitive_cylinder(12, 2, 0.4, 1.2)
+    cv, cn = O.transform(fc[:, :, 0], fc[:, :, 1], tina.translate([1.1, 0, 0]))
+    flags = O.SMOOTHING | O.TEXTURING | O.CULLING | O.CLIPPING
+    c2 = lambda a: np.ascontiguousarray(a[:, :, :2])  # noqa: E731
+    ref = O.render_scene([(fs[:, :, 0], fs[:, :, 1], c2(fs[:, :, 2]), tina.Classic()),
+                          (cv, cn, c2(fc[:, :, 2]), tina.Diffuse(color=[0.8, 0.5, 0.3]))], W, H, view, proj, scene.lighting, flags)
+    assert np.array_equal(scene.engine.depth.to_numpy(), ref['depth']) and (ref['depth'] < 2**30).sum() > 2000
+    assert np.abs(scene.img.to_numpy() - ref['image']).max() <= COLOR_TOL
+    # ConnectiveMesh == MeshModel with (v, v, v) index triples
+    obj = scenes.load_monkey()
+    n = len(obj['v'])
+    rng = np.random.default_rng(3)
+    vn = rng.normal(size=(n, 3)).astype(np.float32)
+    vt = rng.random((n, 2)).astype(np.float32)
+    conn = tina.ConnectiveMesh()
+    conn.set_vertices(obj['v']), conn.set_vert_norms(vn), conn.set_vert_coors(vt), conn.set_faces(obj['f'][:, :, 0])
+    model = tina.MeshModel({'v': obj['v'], 'vn': vn, 'vt': vt, 'f': np.repeat(obj['f'][:, :, :1], 3, axis=2)})
+    imgs = []
+    for mesh in (conn, model):
+        sc = tina.Scene((96, 96), smoothing=True, texturing=True)
+        sc.add_object(mesh, tina.Classic())
+        sc.engine.set_camera(*scenes.default_camera())
+        sc.render()
+        torch.cuda.synchronize()
+        imgs.append((sc.img.to_numpy(), sc.engine.depth.to_numpy()))
+    assert np.array_equal(imgs[0][0], imgs[1][0]) and np.array_equal(imgs[0][1], imgs[1][1]) and (imgs[0][1] < 2**30).sum() > 1000
+
+
 def test_reference_ssr_script_flow(tina):
     """The reference's own tests/ssr.py without its GUI: Scene(ssr=True, taa=True), PBR materials driven by tina.Param,
     a transformed MeshGrid as the mirror plane, the SSR fields set every frame, TAA accumulation over a few frames."""
