@@ -86,6 +86,8 @@ enum {
     TINA_OP_ADD = 9,     /* pop b, a; push a+b                                         material.py:204-220 */
     TINA_OP_REG = 10,    /* push register[arg] (written by the per-pixel prologue program)               */
     TINA_OP_STORE = 11,  /* pop -> register[arg]                                                         */
+    TINA_OP_BCAST = 12,  /* pop v; push (v[arg], v[arg], v[arg])   (uv.x / uv.y of LerpTexture)   nodes.py:129-136 */
+    TINA_OP_CHESS = 13,  /* pop size, uv; push ((uv // size).sum() % 2) broadcast (ChessboardTexture) nodes.py:114-126 */
 };
 #define TINA_MAX_REGS 8
 /* Three-address prologue (TinaMaterial.prologue_form = 2), produced by the host compiler from the postfix prologue: one

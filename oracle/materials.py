@@ -18,6 +18,7 @@ import numpy as np
 
 MAX_LIGHTS, MAX_INSTR, MAX_TEX = 16, 96, 4
 (OP_CONST, OP_INPUT, OP_TEXTURE, OP_FRESNEL, OP_LAMBERT, OP_PHONG, OP_COOK, OP_MIX, OP_MUL, OP_ADD) = range(10)
+OP_BCAST, OP_CHESS = 12, 13  # (10 / 11 are the product's register ops, unused by the unfolded programs here)
 INPUTS = {'pos': 0, 'color': 1, 'normal': 2, 'texcoord': 3}  # matr/nodes.py:79-96
 
 
@@ -124,6 +125,21 @@ def _value(P, node):
         for key in ('metallic', 'albedo', 'specular'):
             _value(P, _param(node, key))
         P.op(OP_FRESNEL)
+    elif k == 'ChessboardTexture':  # nodes.py:114-126: lerp((texcoord // size).sum() % 2, color0, color1)
+        _value(P, _param(node, 'texcoord'))
+        _value(P, _param(node, 'size'))
+        P.op(OP_CHESS)
+        _value(P, _param(node, 'color0'))
+        _value(P, _param(node, 'color1'))
+        P.op(OP_MIX)
+    elif k == 'LerpTexture':  # nodes.py:129-136: lerp(uv.x, x0, x1) + lerp(uv.y, x0, x1)
+        for comp in (0, 1):
+            _value(P, _param(node, 'texcoord'))
+            P.op(OP_BCAST, comp)
+            _value(P, _param(node, 'x0'))
+            _value(P, _param(node, 'x1'))
+            P.op(OP_MIX)
+        P.op(OP_ADD)
     else:
         raise NotImplementedError(k)
 
@@ -251,6 +267,10 @@ def _is_scalar(node):
         return len(shape) == 2 or (len(shape) == 3 and shape[2] == 1)
     if k == 'FresnelFactor':
         return all(_is_scalar(_param(node, key)) for key in ('metallic', 'albedo', 'specular'))
+    if k == 'ChessboardTexture':
+        return all(_is_scalar(_param(node, key)) for key in ('color0', 'color1'))
+    if k == 'LerpTexture':
+        return all(_is_scalar(_param(node, key)) for key in ('x0', 'x1'))
     return False  # Input: vectors
 
 

@@ -150,9 +150,24 @@ class Matrix:
 
     def __truediv__(s, o): return s._bin(o, Matrix._tdiv)
     def __rtruediv__(s, o): return s._bin(o, Matrix._tdiv, True)
-    def __floordiv__(s, o): return s._bin(o, np.floor_divide)
-    def __rfloordiv__(s, o): return s._bin(o, np.floor_divide, True)
-    def __mod__(s, o): return s._bin(o, np.mod)
+    @staticmethod
+    def _fdiv(a, b):
+        # Taichi lowers float `a // b` to floor(a / b) on the ROUNDED f32 quotient (numpy's floor_divide floors the exact one:
+        # 1.0f // 0.2f is 5 in Taichi, 4 in numpy); integers divide as in Python
+        if _is_int(a) and _is_int(b):
+            return np.floor_divide(a, b)
+        return np.floor(np.true_divide(np.asarray(a, dtype=F32), np.asarray(b, dtype=F32)))
+
+    @staticmethod
+    def _fmod(a, b):
+        if _is_int(a) and _is_int(b):
+            return np.mod(a, b)
+        a, b = np.asarray(a, dtype=F32), np.asarray(b, dtype=F32)
+        return a - b * Matrix._fdiv(a, b)  # Taichi: a % b = a - b * (a // b)
+
+    def __floordiv__(s, o): return s._bin(o, Matrix._fdiv)
+    def __rfloordiv__(s, o): return s._bin(o, Matrix._fdiv, True)
+    def __mod__(s, o): return s._bin(o, Matrix._fmod)
     def __pow__(s, o): return s._bin(o, np.power)
     def __rpow__(s, o): return s._bin(o, np.power, True)
     def __neg__(s): return Matrix(-s.a, _raw=True)

@@ -272,6 +272,18 @@ static void tex_sample(const float *tex, int w, int h, int c, const float *uv, f
     }
 }
 
+static void op_bcast(float *v, int k) {
+    const float c = v[k];
+    v[0] = v[1] = v[2] = c;
+}
+/* nodes.py:114-126: (texcoord // size).sum() % 2 with Taichi's float semantics: a // b = floor(a / b) on the rounded f32
+ * quotient, a % b = a - b * (a // b); the result replaces uv (broadcast) */
+static void op_chess(float *uv, const float *size) {
+    const float t = floorf(uv[0] / size[0]) + floorf(uv[1] / size[1]);
+    const float m = t - 2.0f * floorf(t / 2.0f);
+    uv[0] = uv[1] = uv[2] = m;
+}
+
 #define STK 16
 /* evaluate one postfix program; see include/tina_b200.h for the op table */
 static void run_program(const TinaMaterial *m, const float *const *texhost, int begin, int n, const ShadeInputs *in,
@@ -360,6 +372,13 @@ static void run_program(const TinaMaterial *m, const float *const *texhost, int 
             sp -= 1;
             break;
         }
+        case TINA_OP_BCAST: /* uv.x / uv.y of LerpTexture, nodes.py:129-136 */
+            op_bcast(st[sp - 1], I->arg);
+            break;
+        case TINA_OP_CHESS: /* ChessboardTexture's factor, nodes.py:114-126 */
+            op_chess(st[sp - 2], st[sp - 1]);
+            sp -= 1;
+            break;
         }
     }
     for (int k = 0; k < 3; k++) out[k] = sp > 0 ? st[sp - 1][k] : 0.0f;
@@ -927,6 +946,25 @@ static void run_value(const TinaSampleMaterial *m, const float *const *texhost, 
             sp -= 2;
             break;
         }
+        case TINA_OP_MIX: {
+            float *b = st[sp - 1], *a = st[sp - 2], *fac = st[sp - 3];
+            for (int k = 0; k < 3; k++) fac[k] = (1.0f - fac[k]) * a[k] + fac[k] * b[k];
+            sp -= 2;
+            break;
+        }
+        case TINA_OP_ADD: {
+            float *b = st[sp - 1], *a = st[sp - 2];
+            for (int k = 0; k < 3; k++) a[k] = a[k] + b[k];
+            sp -= 1;
+            break;
+        }
+        case TINA_OP_BCAST:
+            op_bcast(st[sp - 1], I->arg);
+            break;
+        case TINA_OP_CHESS:
+            op_chess(st[sp - 2], st[sp - 1]);
+            sp -= 1;
+            break;
         }
     }
     for (int k = 0; k < 3; k++) out[k] = sp > 0 ? st[sp - 1][k] : 0.0f;

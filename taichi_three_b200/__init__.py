@@ -6,7 +6,7 @@ __version__ = (0, 1, 1)
 
 from .matrix import (identity, affine, lookat, ortho, frustum, orthogonal, perspective, scale, translate, quaternion,
                      eularXYZ, euler_matrix, orbit_camera)
-from .material import (Node, Const, Param, Input, Texture, FresnelFactor, IMaterial, MixMaterial, ScaleMaterial,
+from .material import (Node, Const, Param, Input, Texture, ChessboardTexture, LerpTexture, FresnelFactor, IMaterial, MixMaterial, ScaleMaterial,
                        AddMaterial, Lambert, Phong, CookTorrance, Emission, Classic, Diffuse, Lamp, PBR,
                        flatten_material)
 from .assimp import readobj, readgltf, objverts, objnorms, objcoors, objorient, objautoscale

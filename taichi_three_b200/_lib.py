@@ -13,7 +13,7 @@ TINA_COLOR_TONEMAP, TINA_COLOR_FILL_BG, TINA_COLOR_FINISH = 1, 2, 4
 TINA_MAX_LIGHTS, TINA_MAX_INSTR, TINA_MAX_TEX = 16, 96, 4
 
 (OP_CONST, OP_INPUT, OP_TEXTURE, OP_FRESNEL, OP_LAMBERT, OP_PHONG, OP_COOK, OP_MIX, OP_MUL,
- OP_ADD, OP_REG, OP_STORE) = range(12)
+ OP_ADD, OP_REG, OP_STORE, OP_BCAST, OP_CHESS) = range(14)
 TINA_MAX_REGS = 8
 OP3 = 0x100  # three-address prologue form (include/tina_b200.h)
 TINA_VM_VALUES = 16

@@ -148,6 +148,18 @@ __device__ __forceinline__ V3 op_mix_fast(V3 f, V3 a, V3 b) {
     return v3(fmaf(f.x, b.x, (1.0f - f.x) * a.x), fmaf(f.y, b.y, (1.0f - f.y) * a.y), fmaf(f.z, b.z, (1.0f - f.z) * a.z));
 }
 
+__device__ __forceinline__ V3 op_bcast(V3 v, int k) { // uv.x / uv.y of LerpTexture (nodes.py:129-136), broadcast
+    const float c = k == 0 ? v.x : k == 1 ? v.y : v.z;
+    return v3(c, c, c);
+}
+// ChessboardTexture's mix factor (nodes.py:114-126): (texcoord // size).sum() % 2 with Taichi's float semantics,
+// a // b = floor(a / b) on the rounded quotient and a % b = a - b * (a // b)
+__device__ __forceinline__ V3 op_chess(V3 uv, V3 size) {
+    const float t = floorf(uv.x / size.x) + floorf(uv.y / size.y);
+    const float m = t - 2.0f * floorf(t / 2.0f);
+    return v3(m, m, m);
+}
+
 #define STK 12
 __device__ V3 run_program(const TinaMaterial &m, int begin, int n, const ShadeIn &in, V3 nrm, V3 idir, V3 odir, V3 *regs) {
     V3 st[STK];
@@ -214,6 +226,13 @@ __device__ V3 run_program(const TinaMaterial &m, int begin, int n, const ShadeIn
             st[sp - 1] = v3(a.x + b.x, a.y + b.y, a.z + b.z);
             break;
         }
+        case TINA_OP_BCAST:
+            st[sp - 1] = op_bcast(st[sp - 1], I.arg);
+            break;
+        case TINA_OP_CHESS:
+            sp -= 1;
+            st[sp - 1] = op_chess(st[sp - 1], st[sp]);
+            break;
         default:
             break;
         }

@@ -29,7 +29,8 @@ struct WangRNG {
     }
 };
 
-// a parameter program of a TinaSampleMaterial (include/tina_b200.h): TINA_OP_CONST / INPUT / TEXTURE / FRESNEL only
+// a parameter program of a TinaSampleMaterial (include/tina_b200.h): value ops only (CONST / INPUT / TEXTURE / FRESNEL and
+// the MIX / ADD / BCAST / CHESS of the procedural textures)
 #define SSR_STK 8
 __device__ V3 run_value(const TinaSampleMaterial &m, int begin, int n, const ShadeIn &in) {
     V3 st[SSR_STK];
@@ -58,6 +59,25 @@ __device__ V3 run_value(const TinaSampleMaterial &m, int begin, int n, const Sha
             st[sp - 1] = r;
             break;
         }
+        case TINA_OP_MIX: { // (lerp of the procedural textures, nodes.py:114-136)
+            const V3 b = st[sp - 1], a = st[sp - 2], f = st[sp - 3];
+            sp -= 2;
+            st[sp - 1] = op_mix(f, a, b);
+            break;
+        }
+        case TINA_OP_ADD: {
+            const V3 b = st[sp - 1], a = st[sp - 2];
+            sp -= 1;
+            st[sp - 1] = v3(a.x + b.x, a.y + b.y, a.z + b.z);
+            break;
+        }
+        case TINA_OP_BCAST:
+            st[sp - 1] = op_bcast(st[sp - 1], I.arg);
+            break;
+        case TINA_OP_CHESS:
+            sp -= 1;
+            st[sp - 1] = op_chess(st[sp - 1], st[sp]);
+            break;
         default:
             break;
         }

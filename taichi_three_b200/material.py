@@ -121,6 +121,16 @@ class Texture(Node):
         return self._device
 
 
+class ChessboardTexture(Node):  # nodes.py:114-126: lerp((texcoord // size).sum() % 2, color0, color1)
+    arguments = ['texcoord', 'size', 'color0', 'color1']
+    defaults = ['texcoord', 0.1, 0.4, 0.9]
+
+
+class LerpTexture(Node):  # nodes.py:129-136: lerp(uv.x, x0, x1) + lerp(uv.y, x0, x1) (sic: y0 / y1 are unused there)
+    arguments = ['x0', 'x1', 'y0', 'y1', 'texcoord']
+    defaults = [0.0, 1.0, 0.0, 0.0, 'texcoord']
+
+
 class FresnelFactor(Node):  # material.py:69-83
     arguments = ['metallic', 'albedo', 'specular']
     defaults = [0.0, 1.0, 0.5]
@@ -246,6 +256,21 @@ def _emit_value(P, node):
         for key in ('metallic', 'albedo', 'specular'):
             _emit_value(P, node.param(key))
         P.emit(_lib.OP_FRESNEL)
+    elif isinstance(node, ChessboardTexture):  # lerp(fac, color0, color1) = (1 - fac) * color0 + fac * color1 = OP_MIX
+        _emit_value(P, node.param('texcoord'))
+        _emit_value(P, node.param('size'))
+        P.emit(_lib.OP_CHESS)
+        _emit_value(P, node.param('color0'))
+        _emit_value(P, node.param('color1'))
+        P.emit(_lib.OP_MIX)
+    elif isinstance(node, LerpTexture):
+        for comp in (0, 1):
+            _emit_value(P, node.param('texcoord'))
+            P.emit(_lib.OP_BCAST, comp)
+            _emit_value(P, node.param('x0'))
+            _emit_value(P, node.param('x1'))
+            P.emit(_lib.OP_MIX)
+        P.emit(_lib.OP_ADD)
     else:
         raise NotImplementedError(f'material parameter node {type(node).__name__} is not supported by the B200 rasteriser')
 
@@ -336,6 +361,15 @@ def fold_program(code, color_is_one=True):
             stack.append(('c', np.full(3, _INV_PI, dtype=_F)))
         elif op == _lib.OP_TEXTURE:
             push_dyn([stack.pop()], ins)
+        elif op == _lib.OP_BCAST:
+            v = stack.pop()
+            if v[0] == 'c':
+                stack.append(('c', np.full(3, v[1][arg], dtype=_F)))
+            else:
+                push_dyn([v], ins)
+        elif op == _lib.OP_CHESS:
+            size, uv = stack.pop(), stack.pop()
+            push_dyn([uv, size], ins)
         elif op == _lib.OP_PHONG:
             push_dyn([stack.pop()], ins)
         elif op == _lib.OP_COOK:
@@ -382,7 +416,8 @@ _ARITY = {}
 
 def _arity(op):
     return {_lib.OP_CONST: 0, _lib.OP_INPUT: 0, _lib.OP_LAMBERT: 0, _lib.OP_TEXTURE: 1, _lib.OP_PHONG: 1,
-            _lib.OP_COOK: 2, _lib.OP_FRESNEL: 3, _lib.OP_MIX: 3, _lib.OP_MUL: 2, _lib.OP_ADD: 2, _lib.OP_REG: 0}[op]
+            _lib.OP_COOK: 2, _lib.OP_FRESNEL: 3, _lib.OP_MIX: 3, _lib.OP_MUL: 2, _lib.OP_ADD: 2, _lib.OP_REG: 0,
+            _lib.OP_BCAST: 1, _lib.OP_CHESS: 2}[op]
 
 
 def _to_tree(code):
@@ -618,6 +653,10 @@ def _value_is_scalar(node):
         return node.image.shape[2] == 1
     if isinstance(node, FresnelFactor):
         return all(_value_is_scalar(node.param(k)) for k in ('metallic', 'albedo', 'specular'))
+    if isinstance(node, ChessboardTexture):
+        return all(_value_is_scalar(node.param(k)) for k in ('color0', 'color1'))
+    if isinstance(node, LerpTexture):
+        return all(_value_is_scalar(node.param(k)) for k in ('x0', 'x1'))
     return False
 
 

@@ -594,6 +594,42 @@ def case_matgraphs():
     print('matgraphs_random:', len(specs), 'graphs;', os.path.getsize(os.path.join(HERE, 'matgraphs_random.npz')), 'B')
 
 
+def case_proc_textures():
+    """The procedural parameter nodes ChessboardTexture and LerpTexture (matr/nodes.py:114-136; tests/probe.py,
+    examples/meshgrid_cloth.py use them) as colours, mix factors and roughness of the stock materials, shaded by the
+    reference's own sources on the object / lights / camera of case_matgraphs.  Same file layout as matgraphs_random.npz."""
+    ns = {n: getattr(tina, n) for n in ('PBR', 'Classic', 'Diffuse', 'Lamp', 'Lambert', 'Phong', 'Emission', 'CookTorrance', 'Texture',
+                                        'FresnelFactor', 'MixMaterial', 'ScaleMaterial', 'AddMaterial', 'ChessboardTexture', 'LerpTexture')}
+    specs = ['Diffuse(color=LerpTexture(x0=[1.0, 1.0, 1.0], x1=[0.0, 0.0, 1.0]))',
+             'Classic(color=ChessboardTexture(size=0.2, color0=[0.9, 0.2, 0.1], color1=0.8))',
+             'Diffuse(color=ChessboardTexture())',
+             'PBR(basecolor=ChessboardTexture(size=[0.25, 0.125], color0=[0.2, 0.3, 0.9], color1=[0.9, 0.8, 0.2]), metallic=0.3, roughness=LerpTexture(x0=0.1, x1=0.3))',
+             'MixMaterial(ScaleMaterial(Lambert(), [0.8, 0.4, 0.2]), Phong(shineness=12), ChessboardTexture(size=0.3, color0=0.1, color1=0.7))',
+             'AddMaterial(ScaleMaterial(Lambert(), LerpTexture(x0=[0.1, 0.2, 0.3], x1=[0.4, 0.3, 0.2])), ScaleMaterial(Emission(), ChessboardTexture(size=0.15, color0=0.0, color1=0.2)))']
+    out = None
+    for i, spec in enumerate(specs):
+        scene = tina.Scene((36, 30), smoothing=True, texturing=True, tonemap=False)
+        mesh = tina.MeshGrid(9)
+        pos = mesh.pos.to_numpy()
+        xy = pos[..., :2].astype(np.float64)
+        pos[..., 2] = (0.25 * np.sin(4 * xy[..., 0]) * np.cos(3 * xy[..., 1])).astype(np.float32)
+        mesh.pos.from_numpy(pos)
+        scene.add_object(mesh, eval(spec, dict(ns)))
+        scene.lighting.add_light(pos=[0.4, 0.6, 1.5], color=[0.5, 0.7, 0.9])
+        camera(scene, 36 / 30, back=(0.4, 0.7, 2.2))
+        render_and_dump('matgraphs_tmp', scene, [spec])
+        d = dict(np.load(os.path.join(HERE, 'matgraphs_tmp.npz')))
+        if out is None:
+            out = {k: d[k] for k in ('res', 'W2V', 'V2W', 'bias', 'bgcolor', 'light_dirs', 'light_colors', 'ambient', 'verts0', 'norms0',
+                                     'coors0', 'occup0', 'depth', 'flags')}
+            out['nspecs'] = np.int32(len(specs))
+        out[f'spec{i}'] = np.array(spec)
+        out[f'image{i}'] = d['image_pre_tonemap']
+    os.remove(os.path.join(HERE, 'matgraphs_tmp.npz'))
+    np.savez_compressed(os.path.join(HERE, 'matgraphs_proc.npz'), **out)
+    print('matgraphs_proc:', len(specs), 'graphs;', os.path.getsize(os.path.join(HERE, 'matgraphs_proc.npz')), 'B')
+
+
 if __name__ == '__main__':
     np.seterr(all='ignore')
     if len(sys.argv) > 1:  # python make_golden.py micro ...  -> only these cases
@@ -617,3 +653,4 @@ if __name__ == '__main__':
     case_postfx()
     case_setup_cache()
     case_matgraphs()
+    case_proc_textures()

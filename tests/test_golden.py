@@ -31,7 +31,7 @@ def _lighting(tina, g):
 
 
 MATERIAL_NAMES = ('PBR', 'Classic', 'Diffuse', 'Lamp', 'Lambert', 'Phong', 'Emission', 'CookTorrance', 'Texture', 'FresnelFactor',
-                  'MixMaterial', 'ScaleMaterial', 'AddMaterial')
+                  'MixMaterial', 'ScaleMaterial', 'AddMaterial', 'ChessboardTexture', 'LerpTexture')
 
 
 def _material(tina, g, k, key='material'):
@@ -291,6 +291,24 @@ def test_oracle_material_front_end_on_random_graphs(tina, O):
         assert err <= COLOR_TOL, (i, str(g[f'spec{i}']), err)
         kinds |= {n for n in MATERIAL_NAMES if n in str(g[f'spec{i}'])}
     assert kinds >= {'MixMaterial', 'ScaleMaterial', 'AddMaterial', 'CookTorrance', 'Phong', 'Texture', 'FresnelFactor', 'PBR', 'Classic'}
+
+
+def test_oracle_procedural_textures_match_reference_sources(tina, O):
+    """ChessboardTexture / LerpTexture (matr/nodes.py:114-136) as colours, mix factors and roughness, shaded by the reference's
+    own sources (make_golden.py::case_proc_textures): the oracle reproduces every image to 2e-6."""
+    g = np.load(os.path.join(GOLDEN, 'matgraphs_proc.npz'))
+    W, H = (int(v) for v in g['res'])
+    flags = int(g['flags'])
+    lighting = _lighting(tina, g)
+    occup, depth, _, _ = O.render_occup(g['verts0'], g['W2V'], W, H, flags, g['bias'])
+    assert np.array_equal(occup, g['occup0']) and np.array_equal(depth, g['depth'])
+    for i in range(int(g['nspecs'])):
+        image = np.zeros((W, H, 3), np.float32)
+        O.render_color(g['verts0'], g['norms0'], g['coors0'], occup, g['W2V'], g['V2W'], W, H, flags, _material(tina, g, i, 'spec'),
+                       lighting, image, g['bias'])
+        ref = g[f'image{i}']
+        err = (np.abs(image - ref) / np.maximum(1.0, np.abs(ref))).max()
+        assert err <= COLOR_TOL, (i, str(g[f'spec{i}']), err)
 
 
 def test_oracle_setup_cache_matches_reference(O):

@@ -1706,6 +1706,42 @@ def test_random_material_graphs_match_reference_golden(tina):
     assert worst <= COLOR_TOL
 
 
+def test_procedural_textures_match_reference_golden(tina):
+    """ChessboardTexture / LerpTexture nodes (TINA_OP_CHESS / TINA_OP_BCAST in the material programs) against the
+    reference's own shading of six graphs: colour within 1e-4; generic_vm = 1 gives the same pixels."""
+    import os
+    import torch
+    from test_golden import GOLDEN, _lighting, _material
+    g = np.load(os.path.join(GOLDEN, 'matgraphs_proc.npz'))
+    W, H = (int(v) for v in g['res'])
+    flags = int(g['flags'])
+    engine = tina.Engine((W, H))
+    engine.W2V[None], engine.V2W[None], engine.bias[None] = g['W2V'], g['V2W'], g['bias']
+    raster = tina.TriangleRaster(engine, smoothing=bool(flags & 1), texturing=bool(flags & 2))
+    mesh = tina.SimpleMesh()
+    mesh.set_face_verts(g['verts0'])
+    mesh.set_face_norms(g['norms0'])
+    mesh.set_face_coors(g['coors0'])
+    lighting = _lighting(tina, g)
+    for i in range(int(g['nspecs'])):
+        imgs = []
+        for vm in (0, 1):
+            raster.set_tuning(generic_vm=vm)
+            img = tina.Field(torch.zeros((W, H, 3), device='cuda'))
+            engine.clear_depth()
+            raster.set_object(mesh)
+            raster.render_occup()
+            raster.render_color(tina.Shader(img, lighting, _material(tina, g, i, 'spec')))
+            torch.cuda.synchronize()
+            imgs.append(img.to_numpy())
+        ref = g[f'image{i}']
+        err = float((np.abs(imgs[0] - ref) / np.maximum(1.0, np.abs(ref))).max())
+        assert err <= COLOR_TOL, (i, str(g[f'spec{i}']), err)
+        assert np.abs(imgs[0] - imgs[1]).max() <= COLOR_TOL, i
+    with pytest.raises(Exception):
+        tina.LerpTexture(z0=1)
+
+
 def test_setup_cache_fields_match_reference_golden(tina):
     """raster.bcn / can / boo / coo / wsc (triangle.py:25-29), materialised on demand, equal what the reference's
     render_occup stored -- through the expanded-array path and through the indexed (MeshModel) path."""
