@@ -9,7 +9,7 @@ from .matrix import (identity, affine, lookat, ortho, frustum, orthogonal, persp
 from .material import (Node, Const, Param, Input, Texture, ChessboardTexture, LerpTexture, FresnelFactor, IMaterial, MixMaterial, ScaleMaterial,
                        AddMaterial, Lambert, Phong, CookTorrance, Emission, Classic, Diffuse, Lamp, PBR,
                        flatten_material)
-from .assimp import readobj, readgltf, objverts, objnorms, objcoors, objorient, objautoscale
+from .assimp import readobj, readgltf, writeobj, pfmwrite, objverts, objnorms, objcoors, objorient, objautoscale
 from .lighting import Lighting
 from .shader import (IShader, Shader, ShaderGroup, ConstShader, PositionShader, DepthShader, NormalShader,
                      ViewNormalShader, TexcoordShader, ColorShader, ChessboardShader, ViewdirShader, SimpleShader, ProbeShader)

@@ -75,6 +75,44 @@ def readobj(path, orient='xyz', scale=None, simple=False, usemtl=True, quadok=Fa
     return obj
 
 
+def writeobj(path, obj):
+    """assimp/obj.py:103-125: `v` / `vt` / `vn` lines with Python's shortest repr of every coordinate, faces 1-based as
+    v/vt/vn triples ([N, P, 3] index arrays) or the vertex index three times ([N, P]).  `path`: a file name or a writable
+    text stream."""
+    import numpy as np
+    lines = ['# OBJ file saved by tina.writeobj', '# https://github.com/taichi-dev/taichi_three']
+    for tag in ('v', 'vt', 'vn'):
+        if tag in obj:
+            lines += [tag + ' ' + ' '.join(str(x) for x in row) for row in np.asarray(obj[tag])]
+    if 'f' in obj:
+        faces = np.asarray(obj['f'])
+        if faces.ndim >= 3:
+            lines += ['f ' + ' '.join('/'.join(str(i + 1) for i in corner) for corner in face) for face in faces]
+        else:
+            lines += ['f ' + ' '.join('/'.join([str(i + 1)] * 3) for i in face) for face in faces]
+    text = '\n'.join(lines) + '\n'
+    if callable(getattr(path, 'write', None)):
+        path.write(text)
+    else:
+        with open(path, 'w') as fh:
+            fh.write(text)
+
+
+def pfmwrite(path, im):
+    """assimp/pfm.py:4-12: a [W, H(, 3)] float image (x-major like every field here) as a PFM file, rows swapped to y-major,
+    values divided by the largest magnitude, which travels as the (negative = little-endian) scale of the header."""
+    import sys
+    import numpy as np
+    im = np.asarray(im.to_numpy() if hasattr(im, 'to_numpy') else im).swapaxes(0, 1)
+    scale = max(1e-10, float(-im.min()), float(im.max()))
+    h, w = im.shape[:2]
+    with open(path, 'wb') as fh:
+        fh.write(b'PF\n' if im.ndim >= 3 else b'Pf\n')
+        fh.write(f'{w} {h}\n'.encode())
+        fh.write(f'{scale if sys.byteorder == "big" else -scale}\n'.encode())
+        fh.write((im / scale).astype(np.float32).tobytes())
+
+
 def objautoscale(obj):  # obj.py:179-181
     obj['v'] -= np.average(obj['v'], axis=0)
     obj['v'] /= np.max(np.abs(obj['v']))

@@ -90,6 +90,26 @@ def test_loaders(tina):
     assert np.allclose(g.nodes[1].trans[:3, :3] @ [0, 0, 1], [0, -1, 0], atol=1e-6)
 
 
+def test_writeobj_and_pfmwrite_round_trip(tina, tmp_path):
+    """assimp/obj.py:103-125, assimp/pfm.py:4-12: what writeobj saves, readobj loads back; the PFM header and payload."""
+    import io
+    obj = scenes.load_monkey()
+    path = tmp_path / 'm.obj'
+    tina.writeobj(str(path), obj)
+    back = tina.readobj(str(path))
+    assert np.array_equal(back['f'], obj['f']) and np.array_equal(back['v'], obj['v']) and np.array_equal(back['vn'], obj['vn'])
+    buf = io.StringIO()
+    tina.writeobj(buf, {'v': obj['v'][:4], 'f': np.array([[0, 1, 2], [0, 2, 3]])})
+    text = buf.getvalue().splitlines()
+    assert text[0].startswith('# OBJ file saved by tina.writeobj') and text[-1] == 'f 1/1/1 3/3/3 4/4/4'
+    img = np.random.default_rng(0).random((5, 4, 3)).astype(np.float32) * 3
+    tina.pfmwrite(str(tmp_path / 'i.pfm'), img)
+    raw = open(tmp_path / 'i.pfm', 'rb').read()
+    head, w_h, scale, payload = raw.split(b'\n', 3)
+    assert head == b'PF' and w_h == b'5 4' and float(scale) == -float(img.max())
+    assert np.allclose(np.frombuffer(payload, np.float32).reshape(4, 5, 3) * img.max(), img.swapaxes(0, 1), atol=1e-6)
+
+
 def test_camera_matrices(tina):
     p = tina.perspective(60, 16 / 9)
     assert np.isclose(p[1, 1], 1 / np.tan(np.radians(30))) and np.isclose(p[0, 0], p[1, 1] * 9 / 16) and p[3, 2] == -1
